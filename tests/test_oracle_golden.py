@@ -1,0 +1,76 @@
+"""The oracle (oracle/leaf_oracle.py) against the golden vectors made from the real reference.
+
+forward_f32 uses the same ATen CPU ops as the reference, so on the machine/torch build that
+generated the vectors it must match bit for bit; on a different CPU (the GPU box's host) oneDNN
+may pick another kernel, so the portable assertion is 2e-6 relative, and bit-equality is asserted
+only when the reference itself is importable next to it.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import leaf_oracle as O
+from tests.cases import CASES, make_grad_out
+from tests.util import load_golden, rel_err, scaled_err
+
+FWD = [c.name for c in CASES if c.T <= 20000]
+GRAD = [c.name for c in CASES if c.grads]
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_forward_f32_matches_reference_golden(name):
+    case, x, prm, z = load_golden(name)
+    st = O.forward_f32(x, prm, case.K, case.H, compression=case.compression, stages=True)
+    assert st["out"].shape == z["out"].shape
+    assert rel_err(st["out"].numpy(), z["out"], floor=1e-6) < 2e-6
+    assert rel_err(st["p"].numpy(), z["p"], floor=1e-6) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["cfg1_default", "perturbed_F40", "sr22050_evenK", "T161"])
+def test_forward_f32_bit_exact_where_generated(name):
+    import os
+    if not os.path.isdir("/root/reference/leaf_pytorch"):
+        pytest.skip("bit-equality is only claimed on the machine that generated the vectors")
+    case, x, prm, z = load_golden(name)
+    out = O.forward_f32(x, prm, case.K, case.H, compression=case.compression)
+    assert np.array_equal(out.numpy(), z["out"])
+
+
+def test_long_clip_matches_reference_golden():
+    case, x, prm, z = load_golden("long10s")
+    out = O.forward_f32(x, prm, case.K, case.H)
+    assert rel_err(out.numpy(), z["out"], floor=1e-6) < 2e-6
+
+
+@pytest.mark.parametrize("name", ["cfg1_default", "perturbed_F40", "perturbed2_F40", "speech_default",
+                                  "quiet_perturbed", "F80", "sr22050_evenK", "win32_hop8"])
+def test_f64_restatement_bounds_reference_rounding(name):
+    """|f32 reference - f64 maths| is the reference's own rounding.  It is NOT negligible against
+    the 1e-4 target: oneDNN seeds the depthwise accumulator with the bias (1.0) and adds the 401
+    window terms one by one, losing up to ~1.3e-5 of p, and u^q - delta^q cancels ~1.5 digits, so
+    where |out| is small the reference is itself >1e-4 (relative) away from exact arithmetic.
+    Hence every parity assertion in this suite is |d| <= 1e-4*|ref| + 1e-5 (outputs are O(0.1..3))."""
+    case, x, prm, z = load_golden(name)
+    out64 = O.forward_f64(x, prm, case.K, case.H, compression=case.compression).numpy()
+    d = np.abs(z["out"].astype(np.float64) - out64)
+    assert np.all(d <= 1e-4 * np.abs(out64) + 1e-5)
+    assert scaled_err(z["out"], out64) < 1e-5
+
+
+@pytest.mark.parametrize("name", GRAD)
+def test_grads_match_reference_autograd(name):
+    case, x, prm, z = load_golden(name)
+    G = torch.from_numpy(make_grad_out(z["out"].shape, case.seed))
+    g = O.grads_f32(x, prm, case.K, case.H, G)
+    for k in O.PARAM_KEYS:
+        want = z["grad_" + k]
+        assert scaled_err(g[k].reshape(want.shape).numpy(), want) < 1e-5, k
+
+
+def test_geometry_helpers():
+    assert O.window_geometry(16000, 25.0, 10.0) == (401, 160)
+    assert O.window_geometry(22050, 25.0, 10.0) == (552, 220)
+    assert O.same_padding(401) == (200, 200)
+    assert O.same_padding(552) == (275, 276)
+    for T, n in ((15999, 100), (16000, 100), (16001, 101), (161, 2), (1, 1)):
+        assert O.num_frames(T, 401, 160) == n
