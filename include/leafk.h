@@ -1,0 +1,137 @@
+/* leafk.h -- C ABI of libleafk.so, the Blackwell (sm_100a) LEAF frontend kernels.
+ *
+ * This is the drop-in boundary for ONE hot path of SarthakYadav/leaf-pytorch:
+ * leaf_pytorch.frontend.Leaf.forward (reference leaf_pytorch/frontend.py:78-89) and its
+ * parameter-gradient backward (autograd of the same lines, driven from train.py:258).
+ * Every entry point takes plain pointers and sizes; no torch types.  All `const float*`
+ * / `float*` arguments are DEVICE pointers unless the name ends in `_host`.  Nothing here
+ * allocates device memory: scratch comes in through `workspace` (size from
+ * leafk_workspace_bytes) so the caller's allocator (PyTorch's) owns every byte.
+ * Kernels are enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises
+ * the device.  Return value: 0 on success, a negative LEAFK_E* code otherwise, with a
+ * thread-local message available from leafk_last_error().
+ *
+ * Notation: B clips, T samples per clip, F filters, K taps, H hop, N = (T-1)/H + 1 frames.
+ */
+#ifndef LEAFK_H_
+#define LEAFK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEAFK_VERSION 100
+
+#define LEAFK_OK 0
+#define LEAFK_EINVAL (-1)     /* bad shape / null pointer / unsupported geometry            */
+#define LEAFK_EWORKSPACE (-2) /* workspace too small                                         */
+#define LEAFK_ECUDA (-3)      /* a CUDA runtime call or kernel launch failed                 */
+#define LEAFK_EWINDOW (-4)    /* streaming window does not cover the samples the frames need */
+
+/* Which conv kernel computes the Gabor filterbank stage. */
+#define LEAFK_ALGO_AUTO 0
+#define LEAFK_ALGO_FP32 1     /* direct FP32-FMA correlation (CUDA cores)                    */
+#define LEAFK_ALGO_TC 2       /* tcgen05 Toeplitz GEMM, fp16 hi/lo split (3 products), fp32 accumulate */
+
+/* Learnable parameters of the frontend, in the reference's state_dict layout.
+ *   kernel   (F,2)  _complex_conv._kernel      reference convolution.py:58
+ *   pool_w   (F)    _pooling.weights (1,1,F,1) reference pooling.py:18-20
+ *   pool_b   (F)    _pooling._bias  or NULL    reference pooling.py:21-22
+ *   alpha,delta,root (F)  _compression.*       reference postprocessing.py:52-54
+ *   ema_w    (F)    _compression.ema._weights  reference postprocessing.py:11
+ * For compression == 0 (Leaf(pcen_compression=False), frontend.py:74-75) the last four may be NULL. */
+typedef struct leafk_params {
+  const float* kernel;
+  const float* pool_w;
+  const float* pool_b;
+  const float* alpha;
+  const float* delta;
+  const float* root;
+  const float* ema_w;
+} leafk_params;
+
+typedef struct leafk_grads {
+  float* kernel; /* (F,2) */
+  float* pool_w; /* (F)   */
+  float* pool_b; /* (F) or NULL */
+  float* alpha;
+  float* delta;
+  float* root;
+  float* ema_w;
+} leafk_grads;
+
+/* Static configuration: what Leaf.__init__ derives (frontend.py:38-39, 65-73, 84). */
+typedef struct leafk_config {
+  int F;           /* n_filters                                                     */
+  int K;           /* int(sample_rate*window_len//1000 + 1)     frontend.py:38      */
+  int H;           /* int(sample_rate*window_stride//1000)      frontend.py:39      */
+  float pcen_floor;/* 1e-12                                     frontend.py:70      */
+  float clamp_min; /* 1e-5                                      frontend.py:84      */
+  int compression; /* 1: PCEN (frontend.py:65-73)  0: none (frontend.py:74-75)      */
+  int algo;        /* LEAFK_ALGO_*                                                  */
+} leafk_config;
+
+int leafk_version(void);
+const char* leafk_last_error(void);
+
+/* Frames the pooling stage emits for T samples: (T + padL + padR - K)/H + 1 (pooling.py:36-41). */
+int leafk_num_frames(int T, int K, int H);
+
+/* 'same' padding of a K-tap correlation: (K/2 + K%2 - 1, K/2)  (utils.py:5-10). */
+void leafk_same_padding(int K, int* pad_left, int* pad_right);
+
+/* Bytes of device scratch leafk_forward / leafk_forward_window / leafk_backward need for B clips
+ * when producing `n_frames` frames per clip. */
+size_t leafk_workspace_bytes(const leafk_config* cfg, int B, int n_frames);
+
+/* Whole-clip forward: replaces Leaf.forward (frontend.py:78-89).
+ *   x    (B,1,T) contiguous fp32                      -> out (B,F,N) contiguous fp32
+ *   saved_p  optional (B,F,N): floored pooled energies max(pool(.),clamp_min) kept for backward. */
+int leafk_forward(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
+                  float* out, float* saved_p, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Streaming / chunked forward with carried PCEN state (BASELINE.json configs[4]; no reference
+ * analogue: the reference always restarts the EMA at frame 0, postprocessing.py:15).
+ * Produces frames [n_begin, n_begin+n_count) of clips whose full length is T_total, reading a
+ * window of each clip: x_win[b*ldx + i] is sample (t_off + i) of clip b, i in [0,T_win).  The
+ * window must contain every in-clip sample those frames depend on
+ * ([n_begin*H - 2*padL, (n_begin+n_count-1)*H - 2*padL + 2K - 2] clipped to [0,T_total)), else
+ * LEAFK_EWINDOW.  ema_state_in (B,F): smoother state after frame n_begin-1, or NULL to start
+ * from the first produced frame as the reference does; ema_state_out (B,F) or NULL.
+ * out[b*ldo_b + f*ldo_f + (n - n_begin)]; saved_p uses the same strides. */
+int leafk_forward_window(const leafk_config* cfg, const leafk_params* prm, const float* x_win,
+                         int B, long long ldx, long long T_total, long long t_off, int T_win,
+                         int n_begin, int n_count, const float* ema_state_in,
+                         float* ema_state_out, float* out, float* saved_p, long long ldo_b,
+                         long long ldo_f, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Parameter gradients of sum(out * grad_out): replaces autograd through frontend.py:78-89
+ * (train.py:258).  x (B,1,T), grad_out (B,F,N), saved_p (B,F,N) from leafk_forward.  Gradients
+ * are written (not accumulated).  grad_x: optional (B,1,T) or NULL (train.py never needs it). */
+int leafk_backward(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
+                   const float* grad_out, const float* saved_p, const leafk_grads* grads,
+                   float* grad_x, void* workspace, size_t workspace_bytes, void* stream);
+size_t leafk_backward_workspace_bytes(const leafk_config* cfg, int B, int T);
+
+/* End-to-end call on HOST buffers: x_host (B,1,T) and out_host (B,F,N) are host pointers
+ * (pinned for full speed); the library slices the batch into `n_slices` pieces and overlaps
+ * H2D copy / kernels / D2H copy on the two streams given (copy_stream may equal stream).
+ * dev_x (B*T floats), dev_out (B*F*N floats) and workspace are device scratch.  The call
+ * returns after enqueueing; the caller synchronises `stream`. */
+int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B,
+                       int T, float* out_host, int n_slices, float* dev_x, float* dev_out,
+                       void* workspace, size_t workspace_bytes, void* stream, void* copy_stream);
+
+/* 1 when LEAFK_ALGO_TC covers (F,K,H); LEAFK_ALGO_AUTO falls back to LEAFK_ALGO_FP32 otherwise. */
+int leafk_tc_supported(int F, int K, int H);
+
+/* Introspection used by tests / bench: kernels launched by this thread since the last reset. */
+long long leafk_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEAFK_H_ */

@@ -1,0 +1,93 @@
+"""ctypes binding of libleafk.so (C ABI in include/leafk.h).
+
+The library is built in-tree by ``leaf_pytorch_b200/csrc/build.sh`` (or ``__graft_entry__.build()``)
+into ``leaf_pytorch_b200/lib/libleafk.so``.  There is deliberately NO fallback: if the library is
+missing or a call fails, a ``LeafNativeError`` is raised -- the frontend never silently runs torch
+ops instead of the sm_100a kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libleafk.so")
+
+ALGO_AUTO, ALGO_FP32, ALGO_TC = 0, 1, 2
+ALGOS = {"auto": ALGO_AUTO, "fp32": ALGO_FP32, "tc": ALGO_TC}
+
+SYMBOLS = (
+    "leafk_version", "leafk_last_error", "leafk_num_frames", "leafk_same_padding",
+    "leafk_workspace_bytes", "leafk_forward", "leafk_forward_window", "leafk_backward",
+    "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported",
+)
+
+
+class LeafNativeError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("kernel", "pool_w", "pool_b", "alpha", "delta", "root", "ema_w")]
+
+
+class Grads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("kernel", "pool_w", "pool_b", "alpha", "delta", "root", "ema_w")]
+
+
+class Config(C.Structure):
+    _fields_ = [("F", C.c_int), ("K", C.c_int), ("H", C.c_int), ("pcen_floor", C.c_float),
+                ("clamp_min", C.c_float), ("compression", C.c_int), ("algo", C.c_int)]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise loudly when it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise LeafNativeError(
+                f"{LIB_PATH} not found: build it with `sh leaf_pytorch_b200/csrc/build.sh` "
+                "(needs nvcc, targets sm_100a). There is no CPU / torch fallback for this path.")
+        L = C.CDLL(LIB_PATH)
+        vp, ll, i, sz = C.c_void_p, C.c_longlong, C.c_int, C.c_size_t
+        L.leafk_version.restype = i
+        L.leafk_last_error.restype = C.c_char_p
+        L.leafk_num_frames.restype = i
+        L.leafk_num_frames.argtypes = [i, i, i]
+        L.leafk_same_padding.restype = None
+        L.leafk_same_padding.argtypes = [i, C.POINTER(i), C.POINTER(i)]
+        L.leafk_workspace_bytes.restype = sz
+        L.leafk_workspace_bytes.argtypes = [C.POINTER(Config), i, i]
+        L.leafk_forward.restype = i
+        L.leafk_forward.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, vp, vp, sz, vp]
+        L.leafk_forward_window.restype = i
+        L.leafk_forward_window.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, ll, ll, ll, i, i, i,
+                                           vp, vp, vp, vp, ll, ll, vp, sz, vp]
+        L.leafk_backward.restype = i
+        L.leafk_backward.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, vp, C.POINTER(Grads),
+                                     vp, vp, sz, vp]
+        L.leafk_backward_workspace_bytes.restype = sz
+        L.leafk_backward_workspace_bytes.argtypes = [C.POINTER(Config), i, i]
+        L.leafk_forward_host.restype = i
+        L.leafk_forward_host.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, i, vp, vp, vp, sz,
+                                         vp, vp]
+        L.leafk_tc_supported.restype = i
+        L.leafk_tc_supported.argtypes = [i, i, i]
+        L.leafk_launch_count.restype = ll
+        L.leafk_launch_count.argtypes = [i]
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().leafk_last_error().decode("utf-8", "replace")
+        raise LeafNativeError(f"{what} failed (code {rc}): {msg}")

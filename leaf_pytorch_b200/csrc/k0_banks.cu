@@ -1,0 +1,125 @@
+// K0: filter-bank prologue.  One tiny launch per forward/backward.
+//
+// Replaces, for the learnable parameters of one Leaf module:
+//   GaborConstraint.forward                 reference convolution.py:15-22
+//   gabor_filters / gabor_impulse_response  reference impulse_responses.py:5-16, 66-71
+//   the re/im interleave                    reference convolution.py:77-90
+//   gaussian_lowpass                        reference impulse_responses.py:74-80
+// The fp32 operation order of those lines is kept (mu*tau is rounded to fp32 BEFORE sin/cos, the
+// envelope argument is (1/(2 sigma^2)) * (-(tau^2)), the result is (norm*carrier)*envelope), so
+// the banks agree with the reference's to an ulp or two of expf/sincosf.
+//
+// Outputs (all in the caller's workspace):
+//   cprm[f][8]      constrained / derived per-filter constants (see CP_* in leafk_common.cuh)
+//   w32[k][c]       fp32 bank, tap-major, channels padded to C2p, taps padded to Kp with zeros
+//   g32[k][f]       fp32 Gaussian pooling windows, tap-major
+//   w16             fp16 hi/lo bank in the tcgen05 shared-memory layout (see k1_tc.cu), optional
+#include "leafk_common.cuh"
+#include "k1_tc_layout.cuh"
+#include <cuda_fp16.h>
+#include <math.h>
+
+namespace leafk {
+
+struct BankConsts {
+  float mu_hi;      // (float)pi
+  float sigma_lo;   // 4*sqrt(2 ln 2)/pi      convolution.py:18
+  float sigma_hi;   // K*sqrt(2 ln 2)/pi      convolution.py:19
+  float sqrt_2pi;   // sqrt(2*pi) as the reference rounds it (impulse_responses.py:6)
+  float pool_lo;    // 2/K                    impulse_responses.py:75
+};
+
+__global__ void __launch_bounds__(128)
+k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool_w, BankConsts bc,
+                int F, int K, int Kp, int C2p, float* __restrict__ cprm, float* __restrict__ w32,
+                float* __restrict__ g32, uint8_t* __restrict__ w16, int tc_cg, int tc_groups) {
+  const int f = blockIdx.x;                 // filter (or a zero-padding channel pair when f >= F)
+  const size_t grp_bytes = tc::b_group_bytes(tc_cg, Kp);
+  if (f >= F) {                             // padded channels: zero taps in both layouts
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+      for (int c = 2 * f; c < 2 * f + 2; ++c) {
+        if (c < C2p) w32[(size_t)k * C2p + c] = 0.f;
+        if (w16 != nullptr && c < tc_cg * tc_groups) {
+          uint8_t* gb = w16 + (size_t)(c / tc_cg) * grp_bytes;
+          *reinterpret_cast<__half*>(gb + tc::b_offset(tc_cg, c % tc_cg, k)) = __float2half_rn(0.f);
+          *reinterpret_cast<__half*>(gb + tc::b_offset(tc_cg, tc_cg + c % tc_cg, k)) = __float2half_rn(0.f);
+        }
+      }
+    }
+    return;
+  }
+  const float mu = fminf(fmaxf(kernel[2 * f], 0.f), bc.mu_hi);
+  const float sg = fminf(fmaxf(kernel[2 * f + 1], bc.sigma_lo), bc.sigma_hi);
+  const float norm = 1.0f / (bc.sqrt_2pi * sg);
+  const float inv2s2 = 1.0f / (2.0f * (sg * sg));
+  const float ps = fminf(fmaxf(pool_w[f], bc.pool_lo), 0.5f);
+  const float den = (ps * 0.5f) * (float)(K - 1);
+  const float centre = (float)(0.5 * (double)(K - 1));
+
+  // power-of-two scale that puts the filter's peak (norm, at tau = 0) in [2^13, 2^14) for the
+  // fp16 hi/lo split; exact, undone in the epilogue.
+  int wexp;
+  (void)frexpf(norm, &wexp);                // norm = m * 2^wexp, m in [0.5,1)
+  const int wshift = 14 - wexp;             // norm * 2^wshift in [2^13, 2^14)
+
+  if (threadIdx.x == 0) {
+    float* c = cprm + (size_t)f * 8;
+    c[CP_MU] = mu;
+    c[CP_SIGMA] = sg;
+    c[CP_NORM] = norm;
+    c[CP_INV2S2] = inv2s2;
+    c[CP_POOLS] = ps;
+    // g_f[k] = exp2(pool_a * (k - centre)^2)
+    c[CP_POOLA] = (float)(-0.5 * 1.4426950408889634 / ((double)den * (double)den));
+    c[CP_WSCALE] = (float)wshift;
+    c[CP_PAD] = 0.f;
+  }
+
+  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    float wr = 0.f, wi = 0.f;
+    if (k < K) {
+      const float tau = (float)(k - K / 2);
+      const float env = expf(inv2s2 * (-(tau * tau)));
+      const float ph = mu * tau;
+      float sn, cs;
+      sincosf(ph, &sn, &cs);
+      wr = (norm * cs) * env;
+      wi = (norm * sn) * env;
+      const float r = ((float)k - centre) / den;
+      g32[(size_t)k * F + f] = expf(-0.5f * (r * r));
+    }
+    w32[(size_t)k * C2p + 2 * f] = wr;
+    w32[(size_t)k * C2p + 2 * f + 1] = wi;
+    if (w16 != nullptr) {
+      // hi/lo fp16 split of the scaled taps; B-operand rows of the channel's group:
+      // [0,CG) = hi halves, [CG,2CG) = lo halves (k1_tc_layout.cuh)
+      const float sc[2] = {ldexpf(wr, wshift), ldexpf(wi, wshift)};
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c = 2 * f + q;
+        uint8_t* gb = w16 + (size_t)(c / tc_cg) * grp_bytes;
+        const __half hi = __float2half_rn(sc[q]);
+        const __half lo = __float2half_rn(sc[q] - __half2float(hi));
+        *reinterpret_cast<__half*>(gb + tc::b_offset(tc_cg, c % tc_cg, k)) = hi;
+        *reinterpret_cast<__half*>(gb + tc::b_offset(tc_cg, tc_cg + c % tc_cg, k)) = lo;
+      }
+    }
+  }
+}
+
+void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
+               float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, cudaStream_t stream) {
+  BankConsts bc;
+  const float root_2ln2 = sqrtf(2.0f * logf(2.0f));
+  bc.mu_hi = (float)M_PI;
+  bc.sigma_lo = (4.0f * root_2ln2) / (float)M_PI;
+  bc.sigma_hi = ((float)K * root_2ln2) / (float)M_PI;
+  bc.sqrt_2pi = sqrtf(2.0f * (float)M_PI);
+  bc.pool_lo = (float)(2.0 / (double)K);
+  int nblk = C2p / 2;
+  if (w16 != nullptr && tc_cg * tc_groups / 2 > nblk) nblk = tc_cg * tc_groups / 2;
+  k0_banks_kernel<<<nblk, 128, 0, stream>>>(kernel, pool_w, bc, F, K, Kp, C2p, cprm, w32, g32, w16, tc_cg,
+                                            tc_groups);
+}
+
+}  // namespace leafk

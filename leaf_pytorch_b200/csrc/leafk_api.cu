@@ -1,0 +1,279 @@
+// extern "C" surface of libleafk.so (declared in include/leafk.h).  Host-side planning only:
+// geometry, workspace carving, kernel selection and launches on the caller's stream.
+#include "../../include/leafk.h"
+#include "leafk_common.cuh"
+#include "k1_tc_layout.cuh"
+#include "k2_pcen_args.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace leafk {
+// k0_banks.cu
+void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
+               float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, cudaStream_t stream);
+// k1_fp32.cu
+cudaError_t launch_k1_fp32(const Geom& g, const float* x, const float* w32, const float* g32,
+                           float* ppart, cudaStream_t stream);
+constexpr int F32_TILE = 512;
+// k1_tc.cu
+bool k1_tc_supported(const Geom& g, const char** why);
+cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm,
+                         float* ppart, int tc_cg, int tc_groups, cudaStream_t stream);
+constexpr int TC_TILE = 1024;
+// k2_pcen.cu
+cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cudaStream_t stream);
+// bwd.cu
+size_t bwd_workspace_bytes(const leafk_config* cfg, int B, int T);
+int bwd_run(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
+            const float* grad_out, const float* saved_p, const leafk_grads* grads, float* grad_x,
+            void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+thread_local char g_err[512] = "";
+thread_local long long g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches += n; }
+
+static int pick_algo(const leafk_config* cfg, const Geom& g) {
+  if (cfg->algo == LEAFK_ALGO_FP32) return LEAFK_ALGO_FP32;
+  const char* why = nullptr;
+  const bool ok = k1_tc_supported(g, &why);
+  if (cfg->algo == LEAFK_ALGO_TC) return ok ? LEAFK_ALGO_TC : -1;
+  return ok ? LEAFK_ALGO_TC : LEAFK_ALGO_FP32;
+}
+
+// Fill the geometry for producing frames [n_begin, n_begin+n_count) of clips of length T_total.
+static int make_geom(const leafk_config* cfg, int B, long long ldx, long long T_total, long long t_off,
+                     int T_win, int n_begin, int n_count, int tile_len, Geom* out) {
+  if (!cfg) return fail(LEAFK_EINVAL, "null config");
+  if (cfg->F < 1 || cfg->K < 2 || cfg->H < 1) return fail(LEAFK_EINVAL, "bad F/K/H (%d,%d,%d)", cfg->F, cfg->K, cfg->H);
+  if (B < 1 || T_total < 1 || T_win < 1) return fail(LEAFK_EINVAL, "bad B/T (%d,%lld,%d)", B, T_total, T_win);
+  if (T_total > (1LL << 30)) return fail(LEAFK_EINVAL, "clip too long (%lld samples)", T_total);
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.F = cfg->F; g.K = cfg->K; g.H = cfg->H;
+  g.padL = cfg->K / 2 + (cfg->K % 2) - 1;            // utils.py:9
+  g.padR = cfg->K / 2;
+  g.C2 = 2 * cfg->F;
+  g.C2p = (g.C2 + 7) / 8 * 8;
+  g.Kp = (cfg->K + 15) / 16 * 16;
+  g.T_total = T_total; g.t_off = t_off; g.T_win = T_win; g.ldx = ldx;
+  g.N_total = (int)((T_total + g.padL + g.padR - g.K) / g.H + 1);
+  if (n_begin < 0 || n_count < 1 || n_begin + n_count > g.N_total)
+    return fail(LEAFK_EINVAL, "frame range [%d,%d) outside [0,%d)", n_begin, n_begin + n_count, g.N_total);
+  g.n_begin = n_begin; g.n_count = n_count;
+  long long lo = (long long)n_begin * g.H - g.padL;
+  long long hi = (long long)(n_begin + n_count - 1) * g.H - g.padL + g.K;   // exclusive
+  g.te_lo = lo < 0 ? 0 : lo;
+  g.te_hi = hi > T_total ? T_total : hi;
+  g.TL = tile_len;
+  g.n_tiles = (int)((g.te_hi - g.te_lo + tile_len - 1) / tile_len);
+  g.SL = (tile_len + g.K - 2) / g.H + 1;
+  // samples of the clip the frames depend on must be inside the window
+  long long xlo = g.te_lo - g.padL, xhi = g.te_hi - 1 - g.padL + g.K - 1;   // inclusive
+  if (xlo < 0) xlo = 0;
+  if (xhi > T_total - 1) xhi = T_total - 1;
+  if (xlo < t_off || xhi >= t_off + T_win)
+    return fail(LEAFK_EWINDOW, "window [%lld,%lld) does not cover needed samples [%lld,%lld]", t_off,
+                t_off + T_win, xlo, xhi);
+  *out = g;
+  return LEAFK_OK;
+}
+
+static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace* w, int* tc_cg, int* tc_groups) {
+  tc::channel_groups(g.C2, tc_groups, tc_cg);
+  size_t off = 0;
+  w->off_cprm = off; off += align256(sizeof(float) * 8 * g.F);
+  w->off_w32 = off;  off += align256(sizeof(float) * (size_t)g.Kp * g.C2p);
+  w->off_g32 = off;  off += align256(sizeof(float) * (size_t)g.K * g.F);
+  w->off_w16 = off;  off += align256(tc::b_group_bytes(*tc_cg, g.Kp) * (size_t)*tc_groups);
+  w->off_ppart = off;
+  const int sl32 = (F32_TILE + g.K - 2) / g.H + 1, sltc = (TC_TILE + g.K - 2) / g.H + 1;
+  size_t a = (size_t)max_tiles_fp32 * sl32, b = (size_t)max_tiles_tc * sltc;
+  off += align256(sizeof(float) * (size_t)g.B * g.F * (a > b ? a : b));
+  w->total = off;
+}
+
+static int tiles_for(const leafk_config* cfg, int n_frames, int tile_len) {
+  // upper bound of the e-range length for n_frames frames
+  long long len = (long long)(n_frames - 1) * cfg->H + cfg->K;
+  return (int)((len + tile_len - 1) / tile_len);
+}
+
+}  // namespace leafk
+
+using namespace leafk;
+
+extern "C" {
+
+int leafk_version(void) { return LEAFK_VERSION; }
+const char* leafk_last_error(void) { return g_err; }
+
+int leafk_num_frames(int T, int K, int H) {
+  if (T < 1 || K < 2 || H < 1) return 0;
+  const int padL = K / 2 + (K % 2) - 1, padR = K / 2;
+  return (T + padL + padR - K) / H + 1;
+}
+
+void leafk_same_padding(int K, int* pad_left, int* pad_right) {
+  if (pad_left) *pad_left = K / 2 + (K % 2) - 1;
+  if (pad_right) *pad_right = K / 2;
+}
+
+size_t leafk_workspace_bytes(const leafk_config* cfg, int B, int n_frames) {
+  if (!cfg || cfg->F < 1 || cfg->K < 2 || cfg->H < 1 || B < 1 || n_frames < 1) return 0;
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.F = cfg->F; g.K = cfg->K; g.H = cfg->H;
+  g.C2 = 2 * cfg->F; g.C2p = (g.C2 + 7) / 8 * 8; g.Kp = (cfg->K + 15) / 16 * 16;
+  Workspace w;
+  int cg, ng;
+  carve(g, tiles_for(cfg, n_frames, F32_TILE), tiles_for(cfg, n_frames, TC_TILE), &w, &cg, &ng);
+  return w.total;
+}
+
+int leafk_forward_window(const leafk_config* cfg, const leafk_params* prm, const float* x_win, int B,
+                         long long ldx, long long T_total, long long t_off, int T_win, int n_begin,
+                         int n_count, const float* ema_state_in, float* ema_state_out, float* out,
+                         float* saved_p, long long ldo_b, long long ldo_f, void* workspace,
+                         size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!cfg || !prm || !x_win || !out || !workspace) return fail(LEAFK_EINVAL, "null pointer argument");
+  if (!prm->kernel || !prm->pool_w) return fail(LEAFK_EINVAL, "null Gabor / pooling parameter");
+  if (cfg->compression && (!prm->alpha || !prm->delta || !prm->root || !prm->ema_w))
+    return fail(LEAFK_EINVAL, "compression=1 needs alpha, delta, root, ema_w");
+  Geom g;
+  int rc = make_geom(cfg, B, ldx, T_total, t_off, T_win, n_begin, n_count, TC_TILE, &g);
+  if (rc) return rc;
+  const int algo = pick_algo(cfg, g);
+  if (algo < 0) {
+    const char* why = "";
+    k1_tc_supported(g, &why);
+    return fail(LEAFK_EINVAL, "LEAFK_ALGO_TC unsupported for this geometry: %s", why);
+  }
+  if (algo == LEAFK_ALGO_FP32) {
+    rc = make_geom(cfg, B, ldx, T_total, t_off, T_win, n_begin, n_count, F32_TILE, &g);
+    if (rc) return rc;
+  }
+  Workspace w;
+  int tc_cg, tc_groups;
+  carve(g, algo == LEAFK_ALGO_FP32 ? g.n_tiles : 0, algo == LEAFK_ALGO_TC ? g.n_tiles : 0, &w, &tc_cg, &tc_groups);
+  if (w.total > workspace_bytes)
+    return fail(LEAFK_EWORKSPACE, "workspace %zu bytes < %zu needed", workspace_bytes, w.total);
+  uint8_t* base = (uint8_t*)workspace;
+  float* cprm = (float*)(base + w.off_cprm);
+  float* w32 = (float*)(base + w.off_w32);
+  float* g32 = (float*)(base + w.off_g32);
+  uint8_t* w16 = base + w.off_w16;
+  float* ppart = (float*)(base + w.off_ppart);
+
+  launch_k0(prm->kernel, prm->pool_w, g.F, g.K, g.Kp, g.C2p, cprm, w32, g32,
+            algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, stream);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0 launch: %s", cudaGetErrorString(err));
+  if (algo == LEAFK_ALGO_TC)
+    err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, stream);
+  else
+    err = launch_k1_fp32(g, x_win, w32, g32, ppart, stream);
+  if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k1 launch: %s", cudaGetErrorString(err));
+  PcenArgs a;
+  a.pool_b = prm->pool_b; a.alpha = prm->alpha; a.delta = prm->delta; a.root = prm->root;
+  a.ema_w = prm->ema_w; a.ema_in = ema_state_in; a.ema_out = ema_state_out; a.out = out;
+  a.saved_p = saved_p; a.ldo_b = ldo_b; a.ldo_f = ldo_f; a.pcen_floor = cfg->pcen_floor;
+  a.clamp_min = cfg->clamp_min; a.compression = cfg->compression;
+  err = launch_k2(g, ppart, a, stream);
+  if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k2 launch: %s", cudaGetErrorString(err));
+  count_launch(3);
+  return LEAFK_OK;
+}
+
+int leafk_forward(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
+                  float* out, float* saved_p, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!cfg) return fail(LEAFK_EINVAL, "null config");
+  const int N = leafk_num_frames(T, cfg->K, cfg->H);
+  if (N < 1) return fail(LEAFK_EINVAL, "bad T/K/H (%d,%d,%d)", T, cfg->K, cfg->H);
+  return leafk_forward_window(cfg, prm, x, B, T, T, 0, T, 0, N, nullptr, nullptr, out, saved_p,
+                              (long long)cfg->F * N, N, workspace, workspace_bytes, stream);
+}
+
+int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B, int T,
+                       float* out_host, int n_slices, float* dev_x, float* dev_out, void* workspace,
+                       size_t workspace_bytes, void* stream_, void* copy_stream_) {
+  if (!cfg || !x_host || !out_host || !dev_x || !dev_out) return fail(LEAFK_EINVAL, "null pointer argument");
+  cudaStream_t stream = (cudaStream_t)stream_, cstream = (cudaStream_t)copy_stream_;
+  const int N = leafk_num_frames(T, cfg->K, cfg->H);
+  if (N < 1 || B < 1) return fail(LEAFK_EINVAL, "bad B/T");
+  if (n_slices < 1) n_slices = 1;
+  if (n_slices > B) n_slices = B;
+  if (n_slices > 16) n_slices = 16;
+  // Slice i: H2D on copy_stream -> event -> kernels on stream -> event -> D2H on copy_stream.
+  // The workspace is shared by all slices (kernels of consecutive slices serialise on `stream`).
+  cudaEvent_t up[16], done[16];
+  int rc = LEAFK_OK;
+  const bool two = (cstream != stream);
+  int made = 0;
+  for (int i = 0; i < n_slices && rc == LEAFK_OK; ++i) {
+    const int b0 = (int)((long long)B * i / n_slices), b1 = (int)((long long)B * (i + 1) / n_slices);
+    const int nb = b1 - b0;
+    if (nb == 0) continue;
+    cudaEventCreateWithFlags(&up[made], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&done[made], cudaEventDisableTiming);
+    cudaError_t e = cudaMemcpyAsync(dev_x + (size_t)b0 * T, x_host + (size_t)b0 * T, sizeof(float) * (size_t)nb * T,
+                                    cudaMemcpyHostToDevice, cstream);
+    if (e != cudaSuccess) { rc = fail(LEAFK_ECUDA, "H2D: %s", cudaGetErrorString(e)); ++made; break; }
+    if (two) { cudaEventRecord(up[made], cstream); cudaStreamWaitEvent(stream, up[made], 0); }
+    rc = leafk_forward(cfg, prm, dev_x + (size_t)b0 * T, nb, T, dev_out + (size_t)b0 * cfg->F * N, nullptr,
+                       workspace, workspace_bytes, stream);
+    if (rc == LEAFK_OK) {
+      if (two) { cudaEventRecord(done[made], stream); cudaStreamWaitEvent(cstream, done[made], 0); }
+      e = cudaMemcpyAsync(out_host + (size_t)b0 * cfg->F * N, dev_out + (size_t)b0 * cfg->F * N,
+                          sizeof(float) * (size_t)nb * cfg->F * N, cudaMemcpyDeviceToHost, two ? cstream : stream);
+      if (e != cudaSuccess) rc = fail(LEAFK_ECUDA, "D2H: %s", cudaGetErrorString(e));
+    }
+    ++made;
+  }
+  if (two && made > 0 && rc == LEAFK_OK) {             // make `stream` wait for the last D2H
+    cudaEvent_t fin;
+    cudaEventCreateWithFlags(&fin, cudaEventDisableTiming);
+    cudaEventRecord(fin, cstream);
+    cudaStreamWaitEvent(stream, fin, 0);
+    cudaEventDestroy(fin);
+  }
+  for (int i = 0; i < made; ++i) { cudaEventDestroy(up[i]); cudaEventDestroy(done[i]); }
+  return rc;
+}
+
+size_t leafk_backward_workspace_bytes(const leafk_config* cfg, int B, int T) { return bwd_workspace_bytes(cfg, B, T); }
+
+int leafk_backward(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
+                   const float* grad_out, const float* saved_p, const leafk_grads* grads, float* grad_x,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  return bwd_run(cfg, prm, x, B, T, grad_out, saved_p, grads, grad_x, workspace, workspace_bytes,
+                 (cudaStream_t)stream);
+}
+
+int leafk_tc_supported(int F, int K, int H) {
+  if (F < 1 || K < 2 || H < 1) return 0;
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  g.F = F; g.K = K; g.H = H; g.C2 = 2 * F; g.Kp = (K + 15) / 16 * 16; g.TL = TC_TILE;
+  g.SL = (TC_TILE + K - 2) / H + 1;
+  const char* why = nullptr;
+  return k1_tc_supported(g, &why) ? 1 : 0;
+}
+
+long long leafk_launch_count(int reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// Shared geometry / workspace layout for the LEAF frontend kernels (sm_100a).
+//
+// Path being replaced: leaf_pytorch.frontend.Leaf.forward, reference frontend.py:78-89.
+// Index conventions follow SURVEY.md Appendix A.1:
+//   y[c,t] = sum_k W[c,k] * x~[t - padL + k]          (convolution.py:92,97; cross-correlation)
+//   e[f,t] = y[2f,t]^2 + y[2f+1,t]^2                  (frontend.py:15-19)
+//   p[f,n] = bias_f + sum_k g_f[k] * e~[f, n*H - padL + k]   (pooling.py:33-41), e~ = 0 outside [0,T)
+//
+// Work decomposition ("tiles"): the e-sample axis of every clip is cut into disjoint tiles of TL
+// samples.  A tile owns no frame: it emits the partial pooled sums of every frame whose window
+// overlaps it (<= SL of them, "slots"), and the PCEN kernel adds the <= ceil(K/TL)+1 partials of a
+// frame in tile order (deterministic, no atomics, no recomputed halo).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace leafk {
+
+struct Geom {
+  int B, F, K, H;
+  int padL, padR;
+  int C2;             // 2F
+  int C2p;            // 2F rounded up to 8 (fp32 path channel padding)
+  int Kp;             // K rounded up to 16 (zero taps)
+  long long T_total;  // clip length in samples
+  long long t_off;    // first sample held by the x window
+  int T_win;          // samples in the window
+  long long ldx;      // row stride of the x window
+  int n_begin, n_count, N_total;
+  long long te_lo, te_hi;  // e-samples [te_lo, te_hi) are needed by frames [n_begin, n_begin+n_count)
+  int TL;                  // tile length in e-samples
+  int n_tiles;             // tiles per clip
+  int SL;                  // slots (frames) a tile can touch
+};
+
+__host__ __device__ inline long long floordiv_ll(long long a, long long b) {
+  return (a >= 0) ? a / b : -((-a + b - 1) / b);
+}
+__host__ __device__ inline long long ceildiv_ll(long long a, long long b) {
+  return floordiv_ll(a + b - 1, b);
+}
+
+// first frame whose pooling window reaches sample ts or later (clamped to n_begin)
+__host__ __device__ inline int first_frame_of(const Geom& g, long long ts) {
+  long long n = ceildiv_ll(ts + g.padL - g.K + 1, g.H);
+  return (int)(n < g.n_begin ? g.n_begin : n);
+}
+// last frame whose pooling window starts at or before sample tl (clamped to the produced range)
+__host__ __device__ inline int last_frame_of(const Geom& g, long long tl) {
+  long long n = floordiv_ll(tl + g.padL, g.H);
+  long long hi = (long long)g.n_begin + g.n_count - 1;
+  return (int)(n > hi ? hi : n);
+}
+
+// ---- workspace layout (all offsets in bytes, 256-aligned) -------------------------------------
+struct Workspace {
+  size_t off_cprm;   // float[F*8]   constrained parameters + derived per-filter constants
+  size_t off_w32;    // float[Kp*C2p] Gabor bank, tap-major ([k][c]), zero padded
+  size_t off_g32;    // float[K*F]   Gaussian pooling windows, tap-major ([k][f])
+  size_t off_w16;    // uint8[...]   fp16 hi/lo bank in UMMA smem layout (tensor-core path)
+  size_t off_ppart;  // float[B*n_tiles*SL*F] partial pooled sums
+  size_t total;
+};
+
+// per-filter constants produced by k0 (float[8] per filter)
+enum { CP_MU = 0, CP_SIGMA = 1, CP_NORM = 2, CP_INV2S2 = 3, CP_POOLS = 4, CP_POOLA = 5, CP_WSCALE = 6, CP_PAD = 7 };
+
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace leafk

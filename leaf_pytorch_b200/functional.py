@@ -1,0 +1,214 @@
+"""Functional entry points over libleafk.so: the fused LEAF forward / backward on CUDA tensors.
+
+``leaf_forward`` is what ``Leaf.forward`` (frontend.py here, reference frontend.py:78-89) calls;
+it is differentiable with respect to the seven frontend parameters (reference train.py:258 only
+ever needs those) and, optionally, the waveform.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _native as N
+
+PCEN_FLOOR = 1e-12     # reference frontend.py:70
+CLAMP_MIN = 1e-5       # reference frontend.py:84
+
+
+@dataclass(frozen=True)
+class LeafSpec:
+    """Static geometry of one frontend (what reference frontend.py:38-39,65-75 fixes at init)."""
+    F: int
+    K: int
+    H: int
+    compression: bool = True
+    algo: str = "auto"
+    pcen_floor: float = PCEN_FLOOR
+    clamp_min: float = CLAMP_MIN
+
+    def config(self) -> N.Config:
+        return N.Config(self.F, self.K, self.H, self.pcen_floor, self.clamp_min, int(self.compression),
+                        N.ALGOS[self.algo])
+
+    def num_frames(self, T: int) -> int:
+        lo = self.K // 2 + self.K % 2 - 1
+        hi = self.K // 2
+        return (T + lo + hi - self.K) // self.H + 1
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_param(name: str, t: Optional[torch.Tensor], numel: int, device) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.device != device:
+        raise ValueError(f"parameter {name} lives on {t.device}, input on {device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"parameter {name} must be float32, got {t.dtype}")
+    if t.numel() != numel:
+        raise ValueError(f"parameter {name} has {t.numel()} elements, expected {numel}")
+    return t.detach().contiguous()
+
+
+def _check_input(x: torch.Tensor) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("input must be a torch.Tensor")
+    if not x.is_cuda:
+        raise N.LeafNativeError(
+            "leaf_pytorch_b200 runs only on CUDA tensors (sm_100a kernels); there is no CPU fallback. "
+            "Move the module and the input to a GPU.")
+    if x.dtype != torch.float32:
+        raise TypeError(f"input must be float32, got {x.dtype}")
+    if x.dim() != 3 or x.shape[1] != 1:
+        raise ValueError(f"input must have shape (B,1,T), got {tuple(x.shape)}")
+    if x.shape[0] < 1 or x.shape[2] < 1:
+        raise ValueError(f"empty input {tuple(x.shape)}")
+    return x.contiguous()
+
+
+def _params_struct(spec: LeafSpec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, device):
+    F = spec.F
+    keep = [
+        _check_param("kernel", kernel, 2 * F, device), _check_param("pool_w", pool_w, F, device),
+        _check_param("pool_b", pool_b, F, device), _check_param("alpha", alpha, F, device),
+        _check_param("delta", delta, F, device), _check_param("root", root, F, device),
+        _check_param("ema_w", ema_w, F, device),
+    ]
+    return N.Params(*[None if t is None else t.data_ptr() for t in keep]), keep
+
+
+def forward_raw(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w,
+                save_p: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """One fused forward on the current stream; no autograd.  Returns (out, saved_p or None)."""
+    L = N.lib()
+    x = _check_input(x)
+    B, _, T = x.shape
+    n = spec.num_frames(T)
+    cfg = spec.config()
+    prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, spec.F, n), dtype=torch.float32, device=x.device)
+        saved = torch.empty_like(out) if save_p else None
+        ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        rc = L.leafk_forward(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(out), _ptr(saved), _ptr(ws),
+                             ws_bytes, _stream_ptr(x.device))
+    N.check(rc, "leafk_forward")
+    del keep
+    return out, saved
+
+
+def forward_window(spec: LeafSpec, x_win, T_total: int, t_off: int, n_begin: int, n_count: int,
+                   kernel, pool_w, pool_b, alpha, delta, root, ema_w, ema_state=None,
+                   out: Optional[torch.Tensor] = None, want_state: bool = True):
+    """Frames [n_begin, n_begin+n_count) of clips of length T_total from a sample window
+    (x_win[b,0,i] = sample t_off+i).  Returns (out (B,F,n_count), new ema state (B,F) or None)."""
+    L = N.lib()
+    x_win = _check_input(x_win)
+    B, _, T_win = x_win.shape
+    cfg = spec.config()
+    prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x_win.device)
+    with torch.cuda.device(x_win.device):
+        if out is None:
+            out = torch.empty((B, spec.F, n_count), dtype=torch.float32, device=x_win.device)
+        if out.dtype != torch.float32 or out.dim() != 3 or out.shape[0] != B or out.shape[1] != spec.F \
+                or out.shape[2] != n_count or out.stride(2) != 1:
+            raise ValueError("out must be a float32 (B,F,n_count) view with unit stride along frames")
+        state_out = None
+        if spec.compression and want_state:
+            state_out = torch.empty((B, spec.F), dtype=torch.float32, device=x_win.device)
+        if ema_state is not None:
+            ema_state = _check_param("ema_state", ema_state, B * spec.F, x_win.device)
+        ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n_count)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x_win.device)
+        rc = L.leafk_forward_window(C.byref(cfg), C.byref(prm), _ptr(x_win), B, T_win, int(T_total), int(t_off),
+                                    T_win, int(n_begin), int(n_count), _ptr(ema_state), _ptr(state_out),
+                                    _ptr(out), None, out.stride(0), out.stride(1), _ptr(ws), ws_bytes,
+                                    _stream_ptr(x_win.device))
+    N.check(rc, "leafk_forward_window")
+    del keep
+    return out, state_out
+
+
+class _LeafFunction(torch.autograd.Function):
+    """autograd node: forward = leafk_forward, backward = leafk_backward (parameter gradients of
+    reference frontend.py:78-89; input gradient only when the waveform requires grad)."""
+
+    @staticmethod
+    def forward(ctx, spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w):
+        need_grad = any(t is not None and t.requires_grad for t in (x, kernel, pool_w, pool_b, alpha, delta, root, ema_w))
+        out, saved = forward_raw(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w, save_p=need_grad)
+        ctx.spec = spec
+        ctx.has_bias = pool_b is not None
+        ctx.has_pcen = alpha is not None
+        tensors = [x, saved, kernel, pool_w] + ([pool_b] if ctx.has_bias else []) + \
+                  ([alpha, delta, root, ema_w] if ctx.has_pcen else [])
+        if need_grad:
+            ctx.save_for_backward(*tensors)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        L = N.lib()
+        spec: LeafSpec = ctx.spec
+        saved = list(ctx.saved_tensors)
+        x, p = saved[0], saved[1]
+        kernel, pool_w = saved[2], saved[3]
+        idx = 4
+        pool_b = None
+        if ctx.has_bias:
+            pool_b = saved[idx]; idx += 1
+        alpha = delta = root = ema_w = None
+        if ctx.has_pcen:
+            alpha, delta, root, ema_w = saved[idx:idx + 4]
+        x = _check_input(x)
+        B, _, T = x.shape
+        cfg = spec.config()
+        prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
+        grad_out = grad_out.contiguous().to(torch.float32)
+        dev = x.device
+        with torch.cuda.device(dev):
+            def z(t):
+                return None if t is None else torch.zeros(t.numel(), dtype=torch.float32, device=dev)
+            g = [z(kernel), z(pool_w), z(pool_b), z(alpha), z(delta), z(root), z(ema_w)]
+            grads = N.Grads(*[None if t is None else t.data_ptr() for t in g])
+            gx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+            ws_bytes = L.leafk_backward_workspace_bytes(C.byref(cfg), B, T)
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+            rc = L.leafk_backward(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(grad_out), _ptr(p),
+                                  C.byref(grads), _ptr(gx), _ptr(ws), ws_bytes, _stream_ptr(dev))
+        N.check(rc, "leafk_backward")
+        del keep
+
+        def shaped(gt, like):
+            return None if gt is None else gt.view(like.shape)
+        return (None, gx, shaped(g[0], kernel), shaped(g[1], pool_w), shaped(g[2], pool_b) if pool_b is not None else None,
+                shaped(g[3], alpha) if alpha is not None else None, shaped(g[4], delta) if delta is not None else None,
+                shaped(g[5], root) if root is not None else None, shaped(g[6], ema_w) if ema_w is not None else None)
+
+
+def leaf_forward(spec: LeafSpec, x, kernel, pool_w, pool_b=None, alpha=None, delta=None, root=None, ema_w=None):
+    """Differentiable fused LEAF forward: (B,1,T) float32 CUDA waveform -> (B,F,N)."""
+    if spec.compression and any(t is None for t in (alpha, delta, root, ema_w)):
+        raise ValueError("compression=True needs alpha, delta, root and ema_w")
+    return _LeafFunction.apply(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w)
+
+
+def tc_supported(F: int, K: int, H: int) -> bool:
+    """True when the tcgen05 kernel covers this geometry (else algo="auto" uses the fp32 kernel)."""
+    return bool(N.lib().leafk_tc_supported(int(F), int(K), int(H)))
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernels launched through libleafk.so by this thread (bench.py's gpu_launches)."""
+    return int(N.lib().leafk_launch_count(int(reset)))

@@ -1,0 +1,121 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors of the real reference
+and against the oracle on the same seeded inputs.
+
+Tolerance (stated by BASELINE.json north_star: 1e-4 relative, fp32):  |got-ref| <= 1e-4*|ref| + 1e-5.
+The absolute term is needed because the reference itself is ~1e-5 (absolute) away from exact
+arithmetic where u^q - delta^q cancels (see tests/test_oracle_golden.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import CASES
+from tests.util import load_golden, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-4, 1e-5
+ALGOS = ["fp32", "tc"]
+SMALL = [c.name for c in CASES if c.T <= 20000 and not c.grads]
+
+
+def build(case, prm, algo, device="cuda"):
+    import leaf_pytorch_b200 as L
+    fe = L.Leaf(n_filters=case.F, sample_rate=case.sr, window_len=case.wlen, window_stride=case.wstride,
+                init_min_freq=case.min_freq, init_max_freq=case.max_freq, pcen_compression=case.compression,
+                use_legacy_complex=case.legacy, algo=algo)
+    sd = {"_complex_conv._kernel": prm["kernel"], "_pooling.weights": prm["pool_w"].reshape(1, 1, -1, 1),
+          "_pooling._bias": prm["pool_b"]}
+    if case.compression:
+        sd.update({"_compression.alpha": prm["alpha"], "_compression.delta": prm["delta"],
+                   "_compression.root": prm["root"], "_compression.ema._weights": prm["ema_w"]})
+    fe.load_state_dict(sd)
+    return fe.to(device)
+
+
+def algo_available(case, algo):
+    if algo != "tc":
+        return True
+    import leaf_pytorch_b200.functional as LF
+    return LF.tc_supported(case.F, case.K, case.H)
+
+
+def assert_close(got, ref, what):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, what
+    assert np.all(np.isfinite(got)) or not np.all(np.isfinite(ref)), f"{what}: non-finite output"
+    d = np.abs(got - ref)
+    lim = RTOL * np.abs(ref) + ATOL
+    worst = np.unravel_index(np.argmax(d - lim), d.shape)
+    assert np.all(d <= lim), (f"{what}: |d|={d[worst]:.3e} at {worst} (ref {ref[worst]:.6e}, got {got[worst]:.6e}); "
+                              f"scaled err {scaled_err(got, ref):.3e}")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("name", SMALL)
+def test_forward_matches_reference_golden(name, algo):
+    case, x, prm, z = load_golden(name)
+    if not algo_available(case, algo):
+        pytest.skip("tensor-core kernel does not cover this geometry (falls back to fp32 under algo=auto)")
+    fe = build(case, prm, algo)
+    with torch.no_grad():
+        out = fe(x.cuda())
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy(), z["out"], f"{name}/{algo}")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("name", ["cfg1_default", "perturbed2_F40", "T161", "sr22050_evenK", "F80"])
+def test_pooled_energies_match(name, algo):
+    """the saved, floored pooled energies (input of PCEN) against the reference's own sub-modules"""
+    import leaf_pytorch_b200.functional as LF
+    case, x, prm, z = load_golden(name)
+    if not algo_available(case, algo):
+        pytest.skip("geometry not covered by the tensor-core kernel")
+    fe = build(case, prm, algo)
+    out, p = LF.forward_raw(fe.spec, x.cuda(), *fe._param_tuple(), save_p=True)
+    torch.cuda.synchronize()
+    got, ref = p.cpu().numpy().astype(np.float64), z["p"].astype(np.float64)
+    assert np.all(np.abs(got - ref) <= 1e-4 * np.abs(ref) + 2e-6)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_long_clip_10s(algo):
+    case, x, prm, z = load_golden("long10s")
+    fe = build(case, prm, algo)
+    with torch.no_grad():
+        out = fe(x.cuda())
+    assert_close(out.cpu().numpy(), z["out"], f"long10s/{algo}")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_deterministic_and_batch_invariant(algo):
+    case, x, prm, z = load_golden("cfg1_default")
+    fe = build(case, prm, algo)
+    xg = x.cuda()
+    with torch.no_grad():
+        a = fe(xg)
+        b = fe(xg)
+        c = fe(xg[1:3].contiguous())
+    assert torch.equal(a, b)
+    assert torch.equal(a[1:3], c)
+
+
+def test_auto_uses_available_kernel_and_counts_launches():
+    import leaf_pytorch_b200 as L
+    case, x, prm, z = load_golden("cfg1_default")
+    fe = build(case, prm, "auto")
+    L.launch_count(reset=True)
+    with torch.no_grad():
+        out = fe(x.cuda())
+    torch.cuda.synchronize()
+    assert L.launch_count() >= 3
+    assert_close(out.cpu().numpy(), z["out"], "auto")
+
+
+def test_cpu_tensor_fails_loudly():
+    import leaf_pytorch_b200 as L
+    fe = L.Leaf()
+    with pytest.raises(L.LeafNativeError):
+        fe(torch.zeros(1, 1, 1600))
