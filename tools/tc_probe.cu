@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(128) probe_kernel(ProbeArgs p) {
     }
     mma_commit(&bar);
   }
-  mbar_wait(&bar, 0);
+  for (long long i = 0; i < 20000000LL; ++i)
+    if (mbar_try_wait(&bar, 0)) break;
   tc_fence_after();
   for (int c0 = 0; c0 < NB; c0 += 16) {
     float v[16];
@@ -99,13 +100,21 @@ struct RateArgs {
   long long* cycles;
 };
 
+__device__ int g_timeout_flag = 0;
+__device__ __forceinline__ bool bounded_wait(uint64_t* bar, uint32_t parity) {
+  for (long long i = 0; i < 20000000LL; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+  g_timeout_flag = 1;
+  return false;
+}
+
 __global__ void __launch_bounds__(128) rate_kernel(RateArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (64 * 1024) / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0;   // zeros: values irrelevant
-  if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init_fence(); }
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   fence_proxy_async_smem();
   tc_fence_before();
@@ -117,8 +126,11 @@ __global__ void __launch_bounds__(128) rate_kernel(RateArgs p) {
   long long t0 = 0, t1 = 0;
   if (tid == 0) {
     t0 = clock64();
-    uint32_t phase = 0;
+    // two barriers, one per accumulator buffer: a batch may complete before the issuing thread
+    // gets to wait on it, so consecutive batches must not share a barrier (phase ABA)
+    uint32_t phase[2] = {0, 0};
     for (int bt = 0; bt < p.batches; ++bt) {
+      if (bt >= 2) { if (!bounded_wait(&bar[bt & 1], phase[bt & 1])) break; phase[bt & 1] ^= 1; }
       for (int ks = 0; ks < p.per_batch; ++ks) {
         const int kk = ks % 26;
         const uint64_t ad = p.toeplitz ? smem_desc(smem_u32(sA) + kk * 32, 16, 128)
@@ -127,10 +139,10 @@ __global__ void __launch_bounds__(128) rate_kernel(RateArgs p) {
         if (p.NB) mma_f16_ss(tmem + (bt & 1) * 256, ad, bd, idesc_f16(M, p.NB), ks > 0);
         if (p.N2) mma_f16_ss(tmem + (bt & 1) * 256, ad, bd, idesc_f16(M, p.N2), 1);
       }
-      mma_commit(&bar);
-      if (bt >= 1) { mbar_wait(&bar, phase); phase ^= 1; }     // keep one batch in flight
+      mma_commit(&bar[bt & 1]);
     }
-    mbar_wait(&bar, phase);
+    bounded_wait(&bar[0], phase[0]);
+    bounded_wait(&bar[1], phase[1]);
     t1 = clock64();
     p.cycles[blockIdx.x] = t1 - t0;
   }
@@ -145,6 +157,7 @@ static size_t b_off(int NB, int n, int k) {   // same formula as k1_tc_layout.cu
 }
 
 int main() {
+  setvbuf(stdout, NULL, _IONBF, 0);
   int dev = 0;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
@@ -274,6 +287,9 @@ int main() {
     }
     cudaFree(dcyc);
   }
+  int tf = 0;
+  CK(cudaMemcpyFromSymbol(&tf, g_timeout_flag, sizeof(int)));
+  if (tf) { printf("a bounded mbarrier wait TIMED OUT\n"); failures++; }
   printf("tc_probe: %s\n", failures ? "FAILURES" : "ALL OK");
   return failures ? 1 : 0;
 }
