@@ -1,6 +1,6 @@
-// Shared-memory operand layouts of the tensor-core (tcgen05) Gabor kernel, shared between the
-// bank prologue (k0, which writes the B operand into global memory already in this layout) and
-// k1_tc.cu (which bulk-copies it into shared memory unchanged).
+// Shared-memory operand layouts and the shared-memory budget of the tensor-core (tcgen05) Gabor
+// kernel.  Used by the bank prologue (k0 writes the B operand into global memory already in this
+// layout), by k1_tc.cu (which copies it into shared memory unchanged) and by the host planner.
 //
 // B operand = Gabor bank of one channel group, fp16, "N x K, K-major, no swizzle" canonical
 // layout: 8x8 core matrices of 128 contiguous bytes (8 rows x 16 B).  Rows n: [0,CG) are the
@@ -10,6 +10,12 @@
 //   byte(n,k) = (k/16)*NB*32 + ((k%16)/8)*NB*16 + (n/8)*128 + (n%8)*16 + (k%8)*2
 // so for k-step s the descriptor is {start = base + s*NB*32, LBO = NB*16 (K direction),
 // SBO = 128 (N direction)}.
+//
+// A operand = NOT materialised.  For phase p (0..7) a linear fp16 copy of the scaled sample window,
+// shifted by p samples, sits in shared memory: copy_p[i] = x~[ts - padL + p + i].  The descriptor
+// {start = copy_p + s*32 B, LBO = 16 B, SBO = 128 B} makes row m of the 128x16 operand read
+// copy_p[8m + 16s .. 8m + 16s + 15]: a Toeplitz matrix whose core matrices overlap in memory
+// (verified exact on B200 by tools/tc_probe.cu).  Row m of phase p is output sample ts + 8m + p.
 #pragma once
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -17,8 +23,11 @@
 namespace leafk {
 namespace tc {
 
-constexpr int KSTEP = 16;          // taps per MMA (kind::f16, K = 16)
-constexpr int MAX_CG = 80;         // channels per CTA group (hi+lo = 160 accumulator columns)
+constexpr int KSTEP = 16;            // taps per MMA (kind::f16, K = 16)
+constexpr int TILE = 1024;           // e-samples per tile: 128 MMA rows x 8 phases
+constexpr int NPHASE = 8;
+constexpr int MAX_CG = 96;           // largest channel group instantiated (NB = 192 accumulator columns)
+constexpr int SMEM_LIMIT = 227 * 1024;
 
 __host__ __device__ inline size_t b_group_bytes(int CG, int Kp) { return (size_t)Kp * (2 * CG) * 2; }
 
@@ -28,14 +37,50 @@ __host__ __device__ inline size_t b_offset(int CG, int n, int k) {
          (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
 }
 
-// channels per group: split C2 channels into the fewest groups of <= MAX_CG channels, each a
-// multiple of 16 (tcgen05 M=128 needs N % 16 == 0)
-__host__ __device__ inline void channel_groups(int C2, int* n_groups, int* CG) {
-  int g = (C2 + MAX_CG - 1) / MAX_CG;
-  int cg = (C2 + g - 1) / g;
-  cg = (cg + 15) / 16 * 16;
-  *n_groups = (C2 + cg - 1) / cg;
-  *CG = cg;
+// Byte offsets of the kernel's dynamic shared memory regions.
+struct SmemPlan {
+  int CL;          // halves per shifted copy: 8*127 + Kp
+  int LX;          // samples staged per tile: CL + 8
+  int acb;         // bytes per copy
+  int off_w, off_acopy, off_st32, off_sth, off_stl, off_pw, off_misc, total;
+};
+
+__host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL) {
+  SmemPlan s;
+  s.CL = 8 * 127 + Kp;
+  s.LX = s.CL + 8;
+  s.acb = s.CL * 2;
+  int off = 0;
+  s.off_w = off;      off += Kp * 2 * CG * 2;
+  s.off_acopy = off;  off += 16 * s.acb;
+  s.off_st32 = off;   off += s.LX * 4;
+  s.off_sth = off;    off += (s.LX * 2 + 15) / 16 * 16;
+  s.off_stl = off;    off += (s.LX * 2 + 15) / 16 * 16;
+  s.off_pw = off;     off += 2 * 8 * SL * (CG / 4) * 4;
+  s.off_misc = (off + 15) / 16 * 16;
+  s.total = s.off_misc + 512;
+  return s;
+}
+
+// slots (frames) one thread's 8 consecutive samples can touch
+__host__ __device__ inline int slots_per_thread(int K, int H) { return (K + 6) / H + 1; }
+
+// Split C2 channels into the fewest groups of CG channels (CG a multiple of 16, <= MAX_CG) whose
+// shared-memory plan fits.  Returns false when no group size fits.
+__host__ __device__ inline bool channel_groups(int C2, int Kp, int SL, int nslot, int* n_groups, int* CG) {
+  const int max_cg = nslot > 3 ? 64 : MAX_CG;
+  for (int g = 1; g <= 64; ++g) {
+    int cg = (C2 + g - 1) / g;
+    cg = (cg + 15) / 16 * 16;
+    if (cg > max_cg) continue;
+    if (smem_plan(cg, Kp, SL).total > SMEM_LIMIT) continue;
+    *n_groups = (C2 + cg - 1) / cg;
+    *CG = cg;
+    return true;
+  }
+  *n_groups = 0;
+  *CG = 16;
+  return false;
 }
 
 }  // namespace tc

@@ -89,7 +89,8 @@ static int make_geom(const leafk_config* cfg, int B, long long ldx, long long T_
 }
 
 static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace* w, int* tc_cg, int* tc_groups) {
-  tc::channel_groups(g.C2, tc_groups, tc_cg);
+  const int sl_tc = (TC_TILE + g.K - 2) / g.H + 1;
+  tc::channel_groups(g.C2, g.Kp, sl_tc, tc::slots_per_thread(g.K, g.H), tc_groups, tc_cg);
   size_t off = 0;
   w->off_cprm = off; off += align256(sizeof(float) * 8 * g.F);
   w->off_w32 = off;  off += align256(sizeof(float) * (size_t)g.Kp * g.C2p);
