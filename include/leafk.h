@@ -128,6 +128,13 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
 /* 1 when LEAFK_ALGO_TC covers (F,K,H); LEAFK_ALGO_AUTO falls back to LEAFK_ALGO_FP32 otherwise. */
 int leafk_tc_supported(int F, int K, int H);
 
+/* Per-kernel device timing for the roofline report: between begin and end every forward issued
+ * by this thread records CUDA events around K0 (bank prologue), K1 (Gabor GEMM + pooling) and K2
+ * (PCEN) on its stream (at most 1024 forwards).  leafk_profile_end synchronises those events and
+ * returns the number of forwards seen and the mean milliseconds of each kernel. */
+void leafk_profile_begin(void);
+int leafk_profile_end(float* ms_k0, float* ms_k1, float* ms_k2);
+
 /* Introspection used by tests / bench: kernels launched by this thread since the last reset. */
 long long leafk_launch_count(int reset);
 

@@ -33,6 +33,20 @@ int bwd_run(const leafk_config* cfg, const leafk_params* prm, const float* x, in
 thread_local char g_err[512] = "";
 thread_local long long g_launches = 0;
 
+// Optional per-kernel timing (bench.py's roofline leg): between leafk_profile_begin() and
+// leafk_profile_end() every forward records 4 events on its stream (start, after K0, K1, K2).
+struct ProfRec { cudaEvent_t ev[4]; };
+thread_local bool g_prof_on = false;
+thread_local ProfRec g_prof[1024];
+thread_local int g_prof_n = 0;
+static void prof_mark(int which, cudaStream_t stream) {
+  if (!g_prof_on || g_prof_n >= 1024) return;
+  if (which == 0)
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&g_prof[g_prof_n].ev[i]);
+  cudaEventRecord(g_prof[g_prof_n].ev[which], stream);
+  if (which == 3) ++g_prof_n;
+}
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -176,15 +190,18 @@ int leafk_forward_window(const leafk_config* cfg, const leafk_params* prm, const
   uint8_t* w16 = base + w.off_w16;
   float* ppart = (float*)(base + w.off_ppart);
 
+  prof_mark(0, stream);
   launch_k0(prm->kernel, prm->pool_w, g.F, g.K, g.Kp, g.C2p, cprm, w32, g32,
             algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, stream);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0 launch: %s", cudaGetErrorString(err));
+  prof_mark(1, stream);
   if (algo == LEAFK_ALGO_TC)
     err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, stream);
   else
     err = launch_k1_fp32(g, x_win, w32, g32, ppart, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k1 launch: %s", cudaGetErrorString(err));
+  prof_mark(2, stream);
   PcenArgs a;
   a.pool_b = prm->pool_b; a.alpha = prm->alpha; a.delta = prm->delta; a.root = prm->root;
   a.ema_w = prm->ema_w; a.ema_in = ema_state_in; a.ema_out = ema_state_out; a.out = out;
@@ -192,6 +209,7 @@ int leafk_forward_window(const leafk_config* cfg, const leafk_params* prm, const
   a.clamp_min = cfg->clamp_min; a.compression = cfg->compression;
   err = launch_k2(g, ppart, a, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k2 launch: %s", cudaGetErrorString(err));
+  prof_mark(3, stream);
   count_launch(3);
   return LEAFK_OK;
 }
@@ -269,6 +287,33 @@ int leafk_tc_supported(int F, int K, int H) {
   g.SL = (TC_TILE + K - 2) / H + 1;
   const char* why = nullptr;
   return k1_tc_supported(g, &why) ? 1 : 0;
+}
+
+void leafk_profile_begin(void) {
+  g_prof_on = true;
+  g_prof_n = 0;
+}
+
+int leafk_profile_end(float* ms_k0, float* ms_k1, float* ms_k2) {
+  g_prof_on = false;
+  double acc[3] = {0, 0, 0};
+  const int n = g_prof_n;
+  for (int r = 0; r < n; ++r) {
+    cudaEventSynchronize(g_prof[r].ev[3]);
+    for (int i = 0; i < 3; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_prof[r].ev[i], g_prof[r].ev[i + 1]);
+      acc[i] += ms;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(g_prof[r].ev[i]);
+  }
+  g_prof_n = 0;
+  if (n > 0) {
+    if (ms_k0) *ms_k0 = (float)(acc[0] / n);
+    if (ms_k1) *ms_k1 = (float)(acc[1] / n);
+    if (ms_k2) *ms_k2 = (float)(acc[2] / n);
+  }
+  return n;
 }
 
 long long leafk_launch_count(int reset) {

@@ -190,6 +190,14 @@ class Leaf(nn.Module):
         """reference frontend.py:78-89, fused."""
         return LF.leaf_forward(self.spec, x, *self._param_tuple())
 
+    def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+                     n_slices: int = 4) -> torch.Tensor:
+        """Inference on host buffers: pinned (B,1,T) in -> pinned (B,F,N) out, H2D / kernels / D2H
+        pipelined over batch slices inside the library (leafk_forward_host).  No autograd."""
+        prm = [None if p is None else p.detach() for p in self._param_tuple()]
+        return LF.forward_host(self.spec, x_host, *prm, out_host=out_host, n_slices=n_slices,
+                               device=self._complex_conv._kernel.device)
+
     def extra_repr(self) -> str:
         s = self._spec
         return f"n_filters={s.F}, taps={s.K}, hop={s.H}, pcen={s.compression}, algo={self.algo}"

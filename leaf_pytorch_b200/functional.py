@@ -204,6 +204,64 @@ def leaf_forward(spec: LeafSpec, x, kernel, pool_w, pool_b=None, alpha=None, del
     return _LeafFunction.apply(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w)
 
 
+_host_cache = {}
+
+
+def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, alpha, delta, root, ema_w,
+                 out_host: Optional[torch.Tensor] = None, n_slices: int = 4, device=None) -> torch.Tensor:
+    """End-to-end call on HOST buffers through leafk_forward_host: the batch is cut into
+    ``n_slices`` pieces whose H2D copy, kernels and D2H copy overlap on two streams.  ``x_host``
+    (B,1,T) float32 CPU (pinned for full speed); returns ``out_host`` (B,F,N) pinned CPU.  The call
+    synchronises the compute stream before returning (the result is on the host)."""
+    L = N.lib()
+    if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 3 or x_host.shape[1] != 1:
+        raise ValueError("x_host must be a float32 CPU tensor of shape (B,1,T)")
+    device = torch.device(device if device is not None else kernel.device)
+    if device.type != "cuda":
+        raise N.LeafNativeError("forward_host needs the parameters on a CUDA device; there is no CPU fallback")
+    x_host = x_host.contiguous()
+    B, _, T = x_host.shape
+    n = spec.num_frames(T)
+    cfg = spec.config()
+    prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, device)
+    if out_host is None:
+        out_host = torch.empty((B, spec.F, n), dtype=torch.float32, pin_memory=True)
+    if out_host.is_cuda or out_host.dtype != torch.float32 or tuple(out_host.shape) != (B, spec.F, n) \
+            or not out_host.is_contiguous():
+        raise ValueError("out_host must be a contiguous float32 CPU tensor of shape (B,F,N)")
+    with torch.cuda.device(device):
+        key = (device.index, B, T, spec.F, n)
+        bufs = _host_cache.get(key)
+        if bufs is None:
+            _host_cache.clear()
+            ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n)
+            bufs = (torch.empty(B * T, dtype=torch.float32, device=device),
+                    torch.empty(B * spec.F * n, dtype=torch.float32, device=device),
+                    torch.empty(ws_bytes, dtype=torch.uint8, device=device), torch.cuda.Stream(device=device))
+            _host_cache[key] = bufs
+        dev_x, dev_out, ws, side = bufs
+        cur = torch.cuda.current_stream(device)
+        side.wait_stream(cur)
+        rc = L.leafk_forward_host(C.byref(cfg), C.byref(prm), C.c_void_p(x_host.data_ptr()), B, T,
+                                  C.c_void_p(out_host.data_ptr()), int(n_slices), _ptr(dev_x), _ptr(dev_out),
+                                  _ptr(ws), ws.numel(), C.c_void_p(cur.cuda_stream), C.c_void_p(side.cuda_stream))
+        N.check(rc, "leafk_forward_host")
+        cur.synchronize()
+    del keep
+    return out_host
+
+
+def profile_begin() -> None:
+    N.lib().leafk_profile_begin()
+
+
+def profile_end():
+    """-> (n_forwards, mean ms of K0, K1, K2)"""
+    a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+    n = N.lib().leafk_profile_end(C.byref(a), C.byref(b), C.byref(c))
+    return int(n), float(a.value), float(b.value), float(c.value)
+
+
 def tc_supported(F: int, K: int, H: int) -> bool:
     """True when the tcgen05 kernel covers this geometry (else algo="auto" uses the fp32 kernel)."""
     return bool(N.lib().leafk_tc_supported(int(F), int(K), int(H)))
