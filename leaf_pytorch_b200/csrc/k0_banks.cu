@@ -107,8 +107,102 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
   }
 }
 
-void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
-               float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------
+// Backward banks.  For every filter three complex banks in the tcgen05 layout (fp16 hi/lo, own
+// power-of-two scale each):  h (kind 0),  tau*h (kind 1, d/dmu up to the factor i),
+// (tau^2/sigma^3 - 1/sigma)*h (kind 2, d/dsigma).  Group layout: see tc::bwd_channel().
+// bprm[f] = {pool exp2 coefficient, shift_y, shift_z, shift_v, sigma, pool_s, 0, 0}.
+__global__ void __launch_bounds__(128)
+k0_banks_bwd_kernel(const float* __restrict__ kernel, const float* __restrict__ pool_w, BankConsts bc, int F,
+                    int K, int Kp, int FB, float* __restrict__ bprm, uint8_t* __restrict__ w16b) {
+  __shared__ float smax[3][4];
+  const int f = blockIdx.x;                          // padded filter index (f >= F: zero banks)
+  const int CG = 6 * FB;
+  const int grp = f / FB, fl = f % FB;
+  uint8_t* gb = w16b + (size_t)grp * tc::b_group_bytes(CG, Kp);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (f >= F) {
+    for (int k = tid; k < Kp; k += blockDim.x)
+      for (int kind = 0; kind < 3; ++kind)
+        for (int ri = 0; ri < 2; ++ri) {
+          const int c = tc::bwd_channel(FB, fl, kind, ri);
+          *reinterpret_cast<__half*>(gb + tc::b_offset(CG, c, k)) = __float2half_rn(0.f);
+          *reinterpret_cast<__half*>(gb + tc::b_offset(CG, CG + c, k)) = __float2half_rn(0.f);
+        }
+    if (tid == 0) {
+      float* bp = bprm + (size_t)f * 8;
+      bp[0] = -1.0f;
+      for (int i = 1; i < 8; ++i) bp[i] = 0.f;
+    }
+    return;
+  }
+  const float mu = fminf(fmaxf(kernel[2 * f], 0.f), bc.mu_hi);
+  const float sg = fminf(fmaxf(kernel[2 * f + 1], bc.sigma_lo), bc.sigma_hi);
+  const float norm = 1.0f / (bc.sqrt_2pi * sg);
+  const float inv2s2 = 1.0f / (2.0f * (sg * sg));
+  const float ps = fminf(fmaxf(pool_w[f], bc.pool_lo), 0.5f);
+  const float den = (ps * 0.5f) * (float)(K - 1);
+  const float inv_s3 = 1.0f / (sg * sg * sg), inv_s = 1.0f / sg;
+
+  // pass 1: peak magnitude of each kind
+  float mx[3] = {0.f, 0.f, 0.f};
+  for (int k = tid; k < K; k += blockDim.x) {
+    const float tau = (float)(k - K / 2);
+    const float a = norm * expf(inv2s2 * (-(tau * tau)));     // |h| (carrier has modulus 1)
+    mx[0] = fmaxf(mx[0], a);
+    mx[1] = fmaxf(mx[1], fabsf(tau) * a);
+    mx[2] = fmaxf(mx[2], fabsf(tau * tau * inv_s3 - inv_s) * a);
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], o));
+    if (lane == 0) smax[q][warp] = mx[q];
+  }
+  __syncthreads();
+  int shift[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float m = fmaxf(fmaxf(smax[q][0], smax[q][1]), fmaxf(smax[q][2], smax[q][3]));
+    int ex = 0;
+    if (m > 0.f) (void)frexpf(m, &ex);
+    shift[q] = (m > 0.f) ? 14 - ex : 0;
+  }
+  if (tid == 0) {
+    float* bp = bprm + (size_t)f * 8;
+    bp[0] = (float)(-0.5 * 1.4426950408889634 / ((double)den * (double)den));
+    bp[1] = (float)shift[0]; bp[2] = (float)shift[1]; bp[3] = (float)shift[2];
+    bp[4] = sg; bp[5] = ps; bp[6] = 0.f; bp[7] = 0.f;
+  }
+  // pass 2: write the banks
+  for (int k = tid; k < Kp; k += blockDim.x) {
+    float v[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    if (k < K) {
+      const float tau = (float)(k - K / 2);
+      const float env = expf(inv2s2 * (-(tau * tau)));
+      float sn, cs;
+      sincosf(mu * tau, &sn, &cs);
+      const float wr = (norm * cs) * env, wi = (norm * sn) * env;
+      const float cs_ = tau * tau * inv_s3 - inv_s;
+      v[0][0] = wr; v[0][1] = wi;
+      v[1][0] = tau * wr; v[1][1] = tau * wi;
+      v[2][0] = cs_ * wr; v[2][1] = cs_ * wi;
+    }
+#pragma unroll
+    for (int kind = 0; kind < 3; ++kind)
+#pragma unroll
+      for (int ri = 0; ri < 2; ++ri) {
+        const float sc = ldexpf(v[kind][ri], shift[kind]);
+        const __half hi = __float2half_rn(sc);
+        const __half lo = __float2half_rn(sc - __half2float(hi));
+        const int c = tc::bwd_channel(FB, fl, kind, ri);
+        *reinterpret_cast<__half*>(gb + tc::b_offset(CG, c, k)) = hi;
+        *reinterpret_cast<__half*>(gb + tc::b_offset(CG, CG + c, k)) = lo;
+      }
+  }
+}
+
+static BankConsts make_consts(int K) {
   BankConsts bc;
   const float root_2ln2 = sqrtf(2.0f * logf(2.0f));
   bc.mu_hi = (float)M_PI;
@@ -116,6 +210,22 @@ void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, i
   bc.sigma_hi = ((float)K * root_2ln2) / (float)M_PI;
   bc.sqrt_2pi = sqrtf(2.0f * (float)M_PI);
   bc.pool_lo = (float)(2.0 / (double)K);
+  return bc;
+}
+
+void bank_bounds(int K, float* mu_hi, float* sigma_lo, float* sigma_hi, float* pool_lo) {
+  const BankConsts bc = make_consts(K);
+  *mu_hi = bc.mu_hi; *sigma_lo = bc.sigma_lo; *sigma_hi = bc.sigma_hi; *pool_lo = bc.pool_lo;
+}
+
+void launch_k0_bwd(const float* kernel, const float* pool_w, int F, int K, int Kp, int FB, int n_groups,
+                   float* bprm, uint8_t* w16b, cudaStream_t stream) {
+  k0_banks_bwd_kernel<<<n_groups * FB, 128, 0, stream>>>(kernel, pool_w, make_consts(K), F, K, Kp, FB, bprm, w16b);
+}
+
+void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
+               float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, cudaStream_t stream) {
+  const BankConsts bc = make_consts(K);
   int nblk = C2p / 2;
   if (w16 != nullptr && tc_cg * tc_groups / 2 > nblk) nblk = tc_cg * tc_groups / 2;
   k0_banks_kernel<<<nblk, 128, 0, stream>>>(kernel, pool_w, bc, F, K, Kp, C2p, cprm, w32, g32, w16, tc_cg,

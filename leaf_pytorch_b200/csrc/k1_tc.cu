@@ -89,10 +89,20 @@ __device__ __forceinline__ void build_copy(tc::Misc* misc, const uint4* sth4, co
   if (lane == 0) mbar_arrive(&misc->a_full[P]);
 }
 
-template <int CG, int NSLOT>
+// Extra arguments of the backward variant (MODE 1): the epilogue turns the three correlations
+// y, z = x*(tau h), v = x*((tau^2/sigma^3 - 1/sigma) h) into the per-filter sums that give the gradients of
+// centre, width and pooling width ("equivalent without forming dW").
+struct TcBwdArgs {
+  const float* dpT;     // (B, N, F) gradient w.r.t. the floored pooled energies, frame-major
+  const float* bprm;    // (Fpad, 8): [0] pooling exp2 coefficient, [1..3] power-of-two shifts of the y,z,v banks
+  float* bpart;         // (ctas_per_group, Fpad, 4) per-CTA partial sums: {S_mu, S_sigma, S_poolw, 0}
+  int Fpad;             // n_groups * FB
+};
+
+template <int CG, int NSLOT, int MODE>
 __global__ void __launch_bounds__(tc::NTHREADS, 1)
 k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restrict__ w16,
-             const float* __restrict__ cprm, float* __restrict__ ppart, int n_groups) {
+             const float* __restrict__ cprm, float* __restrict__ ppart, int n_groups, const TcBwdArgs ba) {
   using namespace tc;
   constexpr int NB = 2 * CG;                 // accumulator columns per stage (hi | lo products)
   constexpr int NST = (512 / NB) > 4 ? 4 : (512 / NB);
@@ -101,7 +111,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   constexpr uint32_t IDESC_CORR = idesc_f16(128, CG);
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  const SmemPlan sp = smem_plan(CG, g.Kp, g.SL);
+  const SmemPlan sp = smem_plan(CG, g.Kp, g.SL, MODE);
   uint8_t* s_w = smem + sp.off_w;
   uint8_t* s_acopy = smem + sp.off_acopy;
   float* s_st32 = reinterpret_cast<float*>(smem + sp.off_st32);
@@ -217,8 +227,8 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         __syncwarp();
       }
     }
-  } else {
-    // =========================================== EPILOGUE =======================================
+  } else if constexpr (MODE == 0) {
+    // =========================================== EPILOGUE (forward) =============================
     const int e = warp, q = e & 3, hh = e >> 2;
     const int etid = tid;                               // 0..255
     const int m = 32 * q + lane;                        // accumulator row
@@ -316,6 +326,121 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         }
       }
     }
+  } else {
+    // =========================================== EPILOGUE (backward) ============================
+    constexpr int FB = CG / 6;                          // filters per group
+    constexpr int FPB = FB / 2;                         // filters per epilogue thread
+    const int e = warp, q = e & 3, hh = e >> 2;
+    const int m = 32 * q + lane;
+    const int fbase = grp * FB + hh * FPB;              // first filter of this thread
+    float pa[FPB];
+    int shy[FPB], shz[FPB], shv[FPB];
+#pragma unroll
+    for (int i = 0; i < FPB; ++i) {
+      const float* bp = ba.bprm + (size_t)(fbase + i) * 8;
+      pa[i] = __ldg(bp + 0);
+      shy[i] = (int)__ldg(bp + 1); shz[i] = (int)__ldg(bp + 2); shv[i] = (int)__ldg(bp + 3);
+    }
+    float a_mu[FPB], a_sg[FPB], a_pw[FPB];
+#pragma unroll
+    for (int i = 0; i < FPB; ++i) { a_mu[i] = 0.f; a_sg[i] = 0.f; a_pw[i] = 0.f; }
+    const float centre = 0.5f * (float)(g.K - 1);
+    const int n_last = g.n_begin + g.n_count - 1;
+    int it = 0;
+    for (long long u = cta_in_grp; u < n_units; u += ctas_per_grp, ++it) {
+      const int b = (int)(u / g.n_tiles), tile = (int)(u % g.n_tiles);
+      const long long ts = g.te_lo + (long long)tile * TILE;
+      const long long te = (ts + TILE < g.te_hi) ? ts + TILE : g.te_hi;
+      const long long tb = ts + 8 * m;
+      const int nb = first_frame_of(g, tb);
+      float dpv[NSLOT][FPB];
+#pragma unroll
+      for (int j = 0; j < NSLOT; ++j) {
+        const int n = nb + j;
+        const bool nok = (n >= g.n_begin) && (n <= n_last);
+        const float* row = ba.dpT + ((size_t)b * g.N_total + (nok ? n : 0)) * g.F;
+#pragma unroll
+        for (int i = 0; i < FPB; ++i) dpv[j][i] = (nok && fbase + i < g.F) ? __ldg(row + fbase + i) : 0.f;
+      }
+      float sy[FPB], sz[FPB], sv[FPB];
+      bool have_scale = false;
+#pragma unroll 1
+      for (int p = 0; p < NPHASE; ++p) {
+        const int gp = it * NPHASE + p;
+        const int st = gp % NST;
+        const long long t = tb + p;
+        float dj[NSLOT];
+#pragma unroll
+        for (int j = 0; j < NSLOT; ++j) {
+          const int n = nb + j;
+          const long long k = t + g.padL - (long long)n * g.H;
+          const bool ok = (k >= 0) && (k < g.K) && (t < te) && (n <= n_last);
+          const float kc = (float)k - centre;
+          dj[j] = ok ? kc * kc : 1.0e30f;
+        }
+        mbar_wait(&misc->acc_full[st], (uint32_t)((gp / NST) & 1));
+        tc_fence_after();
+        if (!have_scale) {                                 // sx of this tile is published before its first phase
+          const int sx = misc->sx_ring[it & 3];
+#pragma unroll
+          for (int i = 0; i < FPB; ++i) {
+            sy[i] = scalbnf(1.0f, -(sx + shy[i])); sz[i] = scalbnf(1.0f, -(sx + shz[i])); sv[i] = scalbnf(1.0f, -(sx + shv[i]));
+          }
+          have_scale = true;
+        }
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + hh * (CG / 2));
+#pragma unroll
+        for (int c = 0; c < FPB / 4; ++c) {
+          float ym[8], yc[8], zm[8], zc[8], vm[8], vc[8];
+          tmem_ld8x2_sync(taddr + 8 * c, taddr + CG + 8 * c, ym, yc);
+          tmem_ld8x2_sync(taddr + FB + 8 * c, taddr + CG + FB + 8 * c, zm, zc);
+          tmem_ld8x2_sync(taddr + 2 * FB + 8 * c, taddr + CG + 2 * FB + 8 * c, vm, vc);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int fi = 4 * c + i;
+            const float yre = (ym[2 * i] + yc[2 * i]) * sy[fi], yim = (ym[2 * i + 1] + yc[2 * i + 1]) * sy[fi];
+            const float zre = (zm[2 * i] + zc[2 * i]) * sz[fi], zim = (zm[2 * i + 1] + zc[2 * i + 1]) * sz[fi];
+            const float vre = (vm[2 * i] + vc[2 * i]) * sv[fi], vim = (vm[2 * i + 1] + vc[2 * i + 1]) * sv[fi];
+            float de = 0.f, dgs = 0.f;
+#pragma unroll
+            for (int j = 0; j < NSLOT; ++j) {
+              const float wgt = ex2_approx(pa[fi] * dj[j]) * dpv[j][fi];
+              de += wgt;
+              dgs = fmaf(wgt, dj[j] < 1.0e29f ? dj[j] : 0.f, dgs);
+            }
+            const float en = fmaf(yre, yre, yim * yim);
+            a_mu[fi] = fmaf(de, yim * zre - yre * zim, a_mu[fi]);
+            a_sg[fi] = fmaf(de, yre * vre + yim * vim, a_sg[fi]);
+            a_pw[fi] = fmaf(en, dgs, a_pw[fi]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&misc->acc_empty[st]);
+      }
+    }
+    // ---- CTA reduction of the 3*FPB sums per thread -> one partial row per filter ----------------
+    float* red = s_pw;                                  // [8 warps][32]
+#pragma unroll
+    for (int i = 0; i < FPB; ++i) {
+      float v0 = a_mu[i], v1 = a_sg[i], v2 = a_pw[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+      }
+      if (lane == 0) { red[e * 32 + 3 * i] = v0; red[e * 32 + 3 * i + 1] = v1; red[e * 32 + 3 * i + 2] = v2; }
+    }
+    named_bar_sync(BAR_EPI, EPI_WARPS * 32);
+    if (tid < 2 * FPB * 3) {
+      const int h2 = tid / (FPB * 3), r = tid % (FPB * 3);
+      float sacc = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) sacc += red[(h2 * 4 + qq) * 32 + r];
+      const int f = grp * FB + h2 * FPB + r / 3;
+      ba.bpart[((size_t)cta_in_grp * ba.Fpad + f) * 4 + (r % 3)] = sacc;
+    }
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
@@ -340,10 +465,57 @@ bool k1_tc_supported(const Geom& g, const char** why) {
 template <int CG, int NSLOT>
 static cudaError_t launch_inst(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
                                int n_groups, int grid, int smem, cudaStream_t stream) {
-  cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
-  k1_tc_kernel<CG, NSLOT><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups);
+  TcBwdArgs none{nullptr, nullptr, nullptr, 0};
+  k1_tc_kernel<CG, NSLOT, 0><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups, none);
   return cudaGetLastError();
+}
+
+template <int CG, int NSLOT>
+static cudaError_t launch_bwd_inst(const Geom& g, const float* x, const uint8_t* w16, int n_groups, int grid,
+                                   const TcBwdArgs& ba, cudaStream_t stream) {
+  const int smem = tc::smem_plan(CG, g.Kp, g.SL, 1).total;
+  cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  k1_tc_kernel<CG, NSLOT, 1><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, nullptr, nullptr, n_groups, ba);
+  return cudaGetLastError();
+}
+
+static int sm_count(cudaError_t* err) {
+  static int n_sm_cached[64] = {0};
+  int dev = 0;
+  *err = cudaGetDevice(&dev);
+  if (*err != cudaSuccess) return 0;
+  if (dev < 64 && n_sm_cached[dev] == 0) {
+    int v = 0;
+    *err = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (*err != cudaSuccess) return 0;
+    n_sm_cached[dev] = v;
+  }
+  return dev < 64 ? n_sm_cached[dev] : 148;
+}
+
+// Backward correlation pass: FB filters per group (16 -> CG 96, 8 -> CG 48).  Returns the number of CTAs per
+// group through *ctas_per_group (rows of bpart the final reduction must add).
+cudaError_t launch_k1_tc_bwd(const Geom& g, const float* x, const uint8_t* w16b, int FB, int n_groups,
+                             const float* dpT, const float* bprm, float* bpart, int* ctas_per_group,
+                             cudaStream_t stream) {
+  cudaError_t err;
+  const int n_sm = sm_count(&err);
+  if (err != cudaSuccess) return err;
+  const long long n_units = (long long)g.B * g.n_tiles;
+  long long per_grp = n_sm / n_groups;
+  if (per_grp < 1) per_grp = 1;
+  if (per_grp > n_units) per_grp = n_units;
+  *ctas_per_group = (int)per_grp;
+  const int grid = (int)(per_grp * n_groups);
+  TcBwdArgs ba{dpT, bprm, bpart, n_groups * FB};
+  const int nslot = tc::slots_per_thread(g.K, g.H);
+  if (FB == 16 && nslot <= 3) return launch_bwd_inst<96, 3>(g, x, w16b, n_groups, grid, ba, stream);
+  if (FB == 8 && nslot <= 3) return launch_bwd_inst<48, 3>(g, x, w16b, n_groups, grid, ba, stream);
+  if (FB == 8 && nslot <= 5) return launch_bwd_inst<48, 5>(g, x, w16b, n_groups, grid, ba, stream);
+  return cudaErrorNotSupported;
 }
 
 template <int CG>
@@ -356,17 +528,9 @@ static cudaError_t launch_cg(int nslot, const Geom& g, const float* x, const uin
 
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
                          int tc_cg, int tc_groups, cudaStream_t stream) {
-  static int n_sm_cached[64] = {0};
-  int dev = 0;
-  cudaError_t err = cudaGetDevice(&dev);
+  cudaError_t err;
+  const int n_sm = sm_count(&err);
   if (err != cudaSuccess) return err;
-  if (dev < 64 && n_sm_cached[dev] == 0) {
-    int v = 0;
-    err = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    if (err != cudaSuccess) return err;
-    n_sm_cached[dev] = v;
-  }
-  const int n_sm = dev < 64 ? n_sm_cached[dev] : 148;
   const long long n_units = (long long)g.B * g.n_tiles;
   long long per_grp = n_sm / tc_groups;
   if (per_grp < 1) per_grp = 1;

@@ -45,7 +45,8 @@ struct SmemPlan {
   int off_w, off_acopy, off_st32, off_sth, off_stl, off_pw, off_misc, total;
 };
 
-__host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL) {
+// mode 0: forward (pooling partial buffers), mode 1: backward (small reduction scratch instead)
+__host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode = 0) {
   SmemPlan s;
   s.CL = 8 * 127 + Kp;
   s.LX = s.CL + 8;
@@ -56,7 +57,7 @@ __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL) {
   s.off_st32 = off;   off += s.LX * 4;
   s.off_sth = off;    off += (s.LX * 2 + 15) / 16 * 16;
   s.off_stl = off;    off += (s.LX * 2 + 15) / 16 * 16;
-  s.off_pw = off;     off += 2 * 8 * SL * (CG / 4) * 4;
+  s.off_pw = off;     off += (mode == 0) ? 2 * 8 * SL * (CG / 4) * 4 : 8 * 32 * 4;
   s.off_misc = (off + 15) / 16 * 16;
   s.total = s.off_misc + 512;
   return s;
@@ -81,6 +82,20 @@ __host__ __device__ inline bool channel_groups(int C2, int Kp, int SL, int nslot
   *n_groups = 0;
   *CG = 16;
   return false;
+}
+
+// Backward pass: a group holds FB filters x 3 kinds (y, dy/dmu, dy/dsigma) x (re, im) = 6*FB channels.
+// Channel of (filter fl in group, kind, ri):  half = fl / (FB/2);  c = half*(3*FB) + kind*FB + (fl % (FB/2))*2 + ri,
+// so each epilogue half (columns [half*3FB, (half+1)*3FB)) sees kind-major blocks of FB columns.
+__host__ __device__ inline int bwd_channel(int FB, int fl, int kind, int ri) {
+  const int hf = FB / 2;
+  return (fl / hf) * (3 * FB) + kind * FB + (fl % hf) * 2 + ri;
+}
+// filters per backward group: 16 (CG = 96) when the plan fits, else 8 (CG = 48); 0 = unsupported
+__host__ __device__ inline int bwd_filters_per_group(int Kp, int nslot) {
+  if (nslot <= 3 && smem_plan(96, Kp, 0, 1).total <= SMEM_LIMIT) return 16;
+  if (nslot <= 5 && smem_plan(48, Kp, 0, 1).total <= SMEM_LIMIT) return 8;
+  return 0;
 }
 
 }  // namespace tc

@@ -1,0 +1,82 @@
+"""GPU parity of the parameter gradients (leafk_backward through autograd) against the reference's own
+autograd (golden vectors) -- SURVEY 8c-v.  Tolerance: max|d| <= 1e-3 * max|g| per parameter tensor
+(the reference's f32 gradients are themselves ~1e-5 from an f64 evaluation of the same graph)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import CASES, make_grad_out
+from tests.test_forward_gpu import build
+from tests.util import load_golden, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+GRAD_CASES = [c.name for c in CASES if c.grads]
+SD = {"kernel": "_complex_conv._kernel", "pool_w": "_pooling.weights", "pool_b": "_pooling._bias",
+      "alpha": "_compression.alpha", "delta": "_compression.delta", "root": "_compression.root",
+      "ema_w": "_compression.ema._weights"}
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_param_grads_match_reference_autograd(name):
+    case, x, prm, z = load_golden(name)
+    fe = build(case, prm, "auto")
+    out = fe(x.cuda())
+    G = torch.from_numpy(make_grad_out(tuple(out.shape), case.seed)).cuda()
+    (out * G).sum().backward()
+    torch.cuda.synchronize()
+    named = dict(fe.named_parameters())
+    worst = {}
+    for k, sk in SD.items():
+        got = named[sk].grad.detach().cpu().numpy().reshape(-1)
+        want = z["grad_" + k].reshape(-1)
+        assert np.all(np.isfinite(got)), k
+        worst[k] = scaled_err(got, want)
+    assert all(v < 1e-3 for v in worst.values()), worst
+    # the typical agreement is two orders better than the bound; keep an eye on it
+    assert np.median(list(worst.values())) < 1e-4, worst
+
+
+def test_backward_is_deterministic_and_clamped_params_get_zero_grad():
+    case, x, prm, z = load_golden("grad_perturbed")
+    fe = build(case, prm, "auto")
+    G = torch.from_numpy(make_grad_out(z["out"].shape, case.seed)).cuda()
+    grads = []
+    for _ in range(2):
+        fe.zero_grad(set_to_none=True)
+        (fe(x.cuda()) * G).sum().backward()
+        grads.append([p.grad.clone() for p in fe.parameters()])
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
+    gk = fe._complex_conv._kernel.grad.cpu().numpy()
+    want = z["grad_kernel"]
+    assert np.array_equal(gk == 0, want == 0)            # same entries gated by the clamps
+
+
+def test_no_pcen_backward():
+    """Leaf(pcen_compression=False): gradients of sum(p*G) for the three conv/pool parameters against the
+    oracle's autograd (the golden 'nopcen' case stores no gradients)."""
+    from oracle import leaf_oracle as O
+    case, x, prm, z = load_golden("nopcen")
+    fe = build(case, prm, "auto")
+    out = fe(x.cuda())
+    G = torch.from_numpy(make_grad_out(tuple(out.shape), 99))
+    (out * G.cuda()).sum().backward()
+    leaves = {k: prm[k].clone().requires_grad_(True) for k in ("kernel", "pool_w", "pool_b")}
+    full = dict(prm); full.update(leaves)
+    ref = O._forward(x, full, case.K, case.H, False, False)
+    (ref * G).sum().backward()
+    named = dict(fe.named_parameters())
+    for k in leaves:
+        got = named[SD[k]].grad.detach().cpu().numpy().reshape(-1)
+        assert scaled_err(got, leaves[k].grad.numpy().reshape(-1)) < 1e-3, k
+
+
+def test_waveform_gradient_is_refused_loudly():
+    import leaf_pytorch_b200 as L
+    case, x, prm, z = load_golden("grad_default")
+    fe = build(case, prm, "auto")
+    xg = x.cuda().requires_grad_(True)
+    out = fe(xg)
+    with pytest.raises(L.LeafNativeError):
+        out.sum().backward()

@@ -1,0 +1,181 @@
+"""The drop-in boundary on CPU (no GPU, no kernels run): constructor surface, parameter names and
+shapes, initial values, error behaviour, C-ABI symbols.  Mirrors what SURVEY 8b lists."""
+import contextlib
+import ctypes
+import io
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import leaf_pytorch_b200 as L
+from leaf_pytorch_b200 import _native
+from tests.cases import CASES_BY_NAME
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXPECTED_KEYS = {
+    "_complex_conv._kernel": lambda F: (F, 2),
+    "_pooling.weights": lambda F: (1, 1, F, 1),
+    "_pooling._bias": lambda F: (F,),
+    "_compression.alpha": lambda F: (F,),
+    "_compression.delta": lambda F: (F,),
+    "_compression.root": lambda F: (F,),
+    "_compression.ema._weights": lambda F: (F,),
+}
+
+
+@pytest.mark.parametrize("F", [8, 40, 64, 80])
+def test_state_dict_layout(F):
+    fe = L.Leaf(n_filters=F)
+    sd = fe.state_dict()
+    assert set(sd) == set(EXPECTED_KEYS)
+    for k, shp in EXPECTED_KEYS.items():
+        assert tuple(sd[k].shape) == shp(F), k
+    assert sum(p.numel() for p in fe.parameters()) == 8 * F
+    assert len(list(fe.buffers())) == 0
+
+
+def test_default_values_and_attributes():
+    fe = L.Leaf()
+    assert fe._preemp is None and fe._instance_norm is None
+    assert float(fe._maximum_val) == pytest.approx(1e-5)
+    assert fe._complex_conv._kernel_size == 401 and fe._complex_conv._filters == 40
+    assert fe._complex_conv.use_legacy_complex is False
+    assert fe._pooling.kernel_size == 401 and fe._pooling.strides == 160 and fe._pooling.in_channels == 40
+    assert fe._compression._floor == pytest.approx(1e-12)
+    assert torch.all(fe._pooling.weights == 0.4) and torch.all(fe._pooling._bias == 1.0)
+    assert torch.allclose(fe._compression.alpha, torch.full((40,), 0.96))
+    assert torch.all(fe._compression.delta == 2.0) and torch.all(fe._compression.root == 2.0)
+    assert torch.allclose(fe._compression.ema._weights, torch.full((40,), 0.04))
+    assert fe.num_frames(16000) == 100 and fe.num_frames(16001) == 101 and fe.num_frames(161) == 2
+
+
+@pytest.mark.parametrize("name", ["cfg1_default", "F64", "F80", "F8", "sr22050_evenK", "sr8000"])
+def test_initial_gabor_parameters_bit_identical_to_reference(name):
+    c = CASES_BY_NAME[name]
+    fe = L.Leaf(n_filters=c.F, sample_rate=c.sr, window_len=c.wlen, window_stride=c.wstride,
+                init_min_freq=c.min_freq, init_max_freq=c.max_freq)
+    want = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))["init_kernel"]
+    assert np.array_equal(fe._complex_conv._kernel.detach().numpy(), want)
+
+
+def test_error_behaviour_matches_reference():
+    with pytest.raises(NotImplementedError):
+        L.Leaf(preemp=True)
+    with pytest.raises(NotImplementedError):
+        L.Leaf(mean_var_norm=True)
+    with pytest.raises(ValueError):
+        L.Leaf(initializer="nonsense")
+    with pytest.raises(NotImplementedError):
+        L.get_frontend({"frontend": {"name": "mel"}, "audio_config": {}})
+    fe = L.Leaf()
+    with pytest.raises(L.LeafNativeError):           # no silent CPU path
+        fe(torch.zeros(2, 1, 800))
+    with pytest.raises(RuntimeError):                # stages are fused, not callable alone
+        fe._complex_conv(torch.zeros(1, 1, 800))
+
+
+def test_string_initializers_consume_rng_like_reference():
+    for name in ("random", "xavier_normal", "kaiming_normal"):
+        torch.manual_seed(3)
+        a = L.Leaf(n_filters=8, initializer=name)._complex_conv._kernel.detach().clone()
+        torch.manual_seed(3)
+        t = torch.randn(8, 2)
+        if name == "xavier_normal":
+            t = torch.nn.init.xavier_normal_(t)
+        elif name == "kaiming_normal":
+            t = torch.nn.init.kaiming_normal_(t)
+        assert torch.equal(a, t)
+    fe = L.Leaf(n_filters=4, initializer=lambda shape: torch.full(shape, 0.5))
+    assert torch.all(fe._complex_conv._kernel == 0.5)
+
+
+def test_get_frontend_reads_reference_config_keys():
+    cfg = {"frontend": {"name": "leaf", "default_args": True, "use_legacy_complex": True},
+           "audio_config": {"sample_rate": 16000}}
+    fe = L.get_frontend(cfg)
+    assert fe._complex_conv.use_legacy_complex is True and fe.spec.F == 40
+    cfg = {"frontend": {"name": "LEAF", "n_filters": 64, "min_freq": 60.0, "max_freq": 7800.0, "pcen_compress": False},
+           "audio_config": {"sample_rate": 16000, "window_len": 25.0, "window_stride": 10.0}}
+    fe = L.get_frontend(cfg)
+    assert fe.spec.F == 64 and fe._compression is None and fe.spec.compression is False
+    assert set(fe.state_dict()) == {"_complex_conv._kernel", "_pooling.weights", "_pooling._bias"}
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "leafk.h")).read()
+    declared = set(re.findall(r"\b(leafk_[a-z_0-9]+)\s*\(", header))
+    declared -= {"leafk_params", "leafk_grads", "leafk_config"}
+    assert declared, "no prototypes found"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in include/leafk.h but not exported"
+    assert set(_native.SYMBOLS) <= declared
+    L_ = _native.lib()
+    assert L_.leafk_version() == 100
+    assert L_.leafk_num_frames(16000, 401, 160) == 100
+    lo, hi = ctypes.c_int(), ctypes.c_int()
+    L_.leafk_same_padding(552, ctypes.byref(lo), ctypes.byref(hi))
+    assert (lo.value, hi.value) == (275, 276)
+    cfg = _native.Config(40, 401, 160, 1e-12, 1e-5, 1, 0)
+    assert L_.leafk_workspace_bytes(ctypes.byref(cfg), 256, 100) > 0
+    assert L_.leafk_tc_supported(40, 401, 160) == 1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "leaf_pytorch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                src = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "oracle" not in src.replace("leaf_oracle", "oracle") or fn == "never", (
+                    f"{fn} mentions the oracle: the product path must not depend on test infrastructure")
+
+
+@pytest.mark.reference
+def test_state_dict_round_trips_with_the_real_reference():
+    sys.path.insert(0, "/root/reference")
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            from leaf_pytorch.frontend import Leaf as RefLeaf
+            ref = RefLeaf(n_filters=40)
+        ours = L.Leaf(n_filters=40)
+        assert list(ref.state_dict()) == list(ours.state_dict())
+        for k, v in ref.state_dict().items():
+            assert tuple(v.shape) == tuple(ours.state_dict()[k].shape)
+            assert torch.equal(v, ours.state_dict()[k]), k           # identical initial values
+        ours.load_state_dict(ref.state_dict())
+        ref.load_state_dict(ours.state_dict())
+    finally:
+        sys.path.remove("/root/reference")
+        for m in [m for m in sys.modules if m.startswith("leaf_pytorch.") or m == "leaf_pytorch"]:
+            del sys.modules[m]
+
+
+@pytest.mark.reference
+def test_reference_classifier_accepts_our_frontend():
+    """models.classifier.Classifier (reference models/classifier.py:7-18) builds unchanged when
+    leaf_pytorch.get_frontend is ours, and its features sub-module has the reference's keys."""
+    sys.path.insert(0, "/root/reference")
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import models.classifier as MC
+            orig = MC.get_frontend
+            MC.get_frontend = L.get_frontend
+            try:
+                cfg = {"frontend": {"name": "leaf", "default_args": True, "use_legacy_complex": True},
+                       "audio_config": {"sample_rate": 16000},
+                       "model": {"arch": "resnet", "num_classes": 35, "model_depth": 18, "pool": "avgpool",
+                                 "type": "multiclass"}}
+                clf = MC.Classifier(cfg)
+            finally:
+                MC.get_frontend = orig
+        assert isinstance(clf.features, L.Leaf)
+        assert {k for k in clf.state_dict() if k.startswith("features.")} == {"features." + k for k in EXPECTED_KEYS}
+    finally:
+        sys.path.remove("/root/reference")
+        for m in [m for m in sys.modules if m.split(".")[0] in ("leaf_pytorch", "models")]:
+            del sys.modules[m]
