@@ -74,3 +74,17 @@ def test_geometry_helpers():
     assert O.same_padding(552) == (275, 276)
     for T, n in ((15999, 100), (16000, 100), (16001, 101), (161, 2), (1, 1)):
         assert O.num_frames(T, 401, 160) == n
+
+
+@pytest.mark.parametrize("name", ["cfg1_default", "perturbed_F40", "perturbed2_F40", "T161", "T1", "sr22050_evenK",
+                                  "F80", "win32_hop8", "nopcen", "quiet_perturbed"])
+@pytest.mark.parametrize("dbl", [False, True])
+def test_c_oracle_matches_reference_golden(name, dbl):
+    """the torch-free C restatement (oracle/leaf_oracle.c) against the reference's golden vectors"""
+    from oracle import c_oracle
+    case, x, prm, z = load_golden(name)
+    out, p = c_oracle.forward(x.numpy(), {k: v.numpy() for k, v in prm.items()}, case.K, case.H,
+                              compression=case.compression, use_double=dbl)
+    d = np.abs(out.astype(np.float64) - z["out"])
+    assert np.all(d <= 1e-4 * np.abs(z["out"]) + 1e-5), float(d.max())
+    assert scaled_err(out, z["out"]) < 2e-5
