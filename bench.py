@@ -296,7 +296,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * T * 4,
                     "d2h_bytes_per_step": world * B * F * n_frames * 4, "ms_per_step": e2e_ms / steps,
-                    "api": "Leaf.forward_host -> leafk_forward_host (pinned host in/out, 4 pipelined slices)"},
+                    "api": "Leaf.forward_host -> leafk_forward_host (pinned host in/out; H2D in 8 slices with ready flags, one persistent launch)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }

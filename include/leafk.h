@@ -117,10 +117,13 @@ int leafk_backward(const leafk_config* cfg, const leafk_params* prm, const float
 size_t leafk_backward_workspace_bytes(const leafk_config* cfg, int B, int T);
 
 /* End-to-end call on HOST buffers: x_host (B,1,T) and out_host (B,F,N) are host pointers
- * (pinned for full speed); the library slices the batch into `n_slices` pieces and overlaps
- * H2D copy / kernels / D2H copy on the two streams given (copy_stream may equal stream).
- * dev_x (B*T floats), dev_out (B*F*N floats) and workspace are device scratch.  The call
- * returns after enqueueing; the caller synchronises `stream`. */
+ * (pinned for full speed).  The H2D copy is enqueued on copy_stream in `n_slices` (<= 64) pieces,
+ * each followed by a stream-ordered 32-bit flag write; ONE persistent launch of the tensor-core
+ * kernel on `stream` consumes clips as their slice lands, so the PCIe transfer and the compute
+ * overlap without per-slice launch overheads; PCEN and the D2H copy follow on `stream`.  When
+ * the FP32 kernel is selected, copy_stream == stream, or the driver lacks cuStreamWriteValue32,
+ * it falls back to per-slice launches.  dev_x (B*T floats), dev_out (B*F*N floats) and workspace
+ * are device scratch.  The call returns after enqueueing; the caller synchronises `stream`. */
 int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B,
                        int T, float* out_host, int n_slices, float* dev_x, float* dev_out,
                        void* workspace, size_t workspace_bytes, void* stream, void* copy_stream);

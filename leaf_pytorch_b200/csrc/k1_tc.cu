@@ -92,6 +92,14 @@ __device__ __forceinline__ void build_copy(tc::Misc* misc, const uint4* sth4, co
 // Extra arguments of the backward variant (MODE 1): the epilogue turns the three correlations
 // y, z = x*(tau h), v = x*((tau^2/sigma^3 - 1/sigma) h) into the per-filter sums that give the gradients of
 // centre, width and pooling width ("equivalent without forming dW").
+// Optional host-pipelining hook: when `ready` is non-null the producers wait, before touching clip b, until
+// ready[b / clips_per_flag] != 0.  The flags are set by stream-ordered 32-bit writes that follow each slice of
+// the H2D copy on another stream, so ONE persistent launch overlaps the whole PCIe transfer (leafk_forward_host).
+struct TcReady {
+  const int* ready;
+  int clips_per_flag;
+};
+
 struct TcBwdArgs {
   const float* dpT;     // (B, N, F) gradient w.r.t. the floored pooled energies, frame-major
   const float* bprm;    // (Fpad, 8): [0] pooling exp2 coefficient, [1..3] power-of-two shifts of the y,z,v banks
@@ -102,7 +110,8 @@ struct TcBwdArgs {
 template <int CG, int NSLOT, int MODE>
 __global__ void __launch_bounds__(tc::NTHREADS, 1)
 k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restrict__ w16,
-             const float* __restrict__ cprm, float* __restrict__ ppart, int n_groups, const TcBwdArgs ba) {
+             const float* __restrict__ cprm, float* __restrict__ ppart, int n_groups, const TcBwdArgs ba,
+             const TcReady rdy) {
   using namespace tc;
   constexpr int NB = 2 * CG;                 // accumulator columns per stage (hi | lo products)
   constexpr int NST = (512 / NB) > 4 ? 4 : (512 / NB);
@@ -155,12 +164,21 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       const int b = (int)(u / g.n_tiles), tile = (int)(u % g.n_tiles);
       const long long ts = g.te_lo + (long long)tile * TILE;
       const float* xrow = x + (size_t)b * g.ldx;
-      named_bar_sync(BAR_PROD, PROD_THREADS);        // staging of the previous tile fully consumed
+      if (rdy.ready != nullptr && ptid == 0) {       // clip b still in flight over PCIe?
+        const int* flag = rdy.ready + b / rdy.clips_per_flag;
+        int v;
+        unsigned spins = 0;
+        do {
+          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          if (v == 0) { __nanosleep(200); if (++spins > (1u << 24)) __trap(); }
+        } while (v == 0);
+      }
+      named_bar_sync(BAR_PROD, PROD_THREADS);        // staging of the previous tile fully consumed; clip b resident
       float mx = 0.f;
       for (int i = ptid; i < sp.LX; i += PROD_THREADS) {
         const long long a = ts - g.padL + i, wi = a - g.t_off;
         float v = 0.f;
-        if (a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win) v = __ldg(xrow + wi);
+        if (a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win) v = xrow[wi];   // coherent load: may have just landed
         s_st32[i] = v;
         mx = fmaxf(mx, fabsf(v));
       }
@@ -314,7 +332,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       const int sx = misc->sx_ring[it & 3];
       float* dst = ppart + ((size_t)b * g.n_tiles + tile) * g.SL * g.F;
       for (int idx = etid; idx < g.SL * (CG / 2); idx += EPI_WARPS * 32) {
-        const int slot = idx / (CG / 2), fl = idx % (CG / 2);
+        const int fl = idx / g.SL, slot = idx % g.SL;       // (filter, slot) layout, slot fastest
         const int h2 = fl / FPT, fi = fl % FPT;
         const int f = grp * (CG / 2) + fl;
         if (f < g.F) {
@@ -322,7 +340,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) s += pw_buf[((size_t)(h2 * 4 + qq) * g.SL + slot) * FPT + fi];
           const int wsh = (int)__ldg(cprm + (size_t)f * 8 + CP_WSCALE);
-          dst[(size_t)slot * g.F + f] = scalbnf(s, -2 * (sx + wsh));
+          dst[(size_t)f * g.SL + slot] = scalbnf(s, -2 * (sx + wsh));
         }
       }
     }
@@ -464,11 +482,11 @@ bool k1_tc_supported(const Geom& g, const char** why) {
 
 template <int CG, int NSLOT>
 static cudaError_t launch_inst(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
-                               int n_groups, int grid, int smem, cudaStream_t stream) {
+                               int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy) {
   cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   TcBwdArgs none{nullptr, nullptr, nullptr, 0};
-  k1_tc_kernel<CG, NSLOT, 0><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups, none);
+  k1_tc_kernel<CG, NSLOT, 0><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups, none, rdy);
   return cudaGetLastError();
 }
 
@@ -478,7 +496,8 @@ static cudaError_t launch_bwd_inst(const Geom& g, const float* x, const uint8_t*
   const int smem = tc::smem_plan(CG, g.Kp, g.SL, 1).total;
   cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
-  k1_tc_kernel<CG, NSLOT, 1><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, nullptr, nullptr, n_groups, ba);
+  k1_tc_kernel<CG, NSLOT, 1><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, nullptr, nullptr, n_groups, ba,
+                                                                   TcReady{nullptr, 1});
   return cudaGetLastError();
 }
 
@@ -520,14 +539,15 @@ cudaError_t launch_k1_tc_bwd(const Geom& g, const float* x, const uint8_t* w16b,
 
 template <int CG>
 static cudaError_t launch_cg(int nslot, const Geom& g, const float* x, const uint8_t* w16, const float* cprm,
-                             float* ppart, int n_groups, int grid, int smem, cudaStream_t stream) {
-  if (nslot <= 3) return launch_inst<CG, 3>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream);
-  if constexpr (CG <= 64) return launch_inst<CG, 5>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream);
+                             float* ppart, int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy) {
+  if (nslot <= 3) return launch_inst<CG, 3>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy);
+  if constexpr (CG <= 64) return launch_inst<CG, 5>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy);
   return cudaErrorNotSupported;
 }
 
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
-                         int tc_cg, int tc_groups, cudaStream_t stream) {
+                         int tc_cg, int tc_groups, cudaStream_t stream, const int* ready, int clips_per_flag) {
+  const TcReady rdy{ready, clips_per_flag < 1 ? 1 : clips_per_flag};
   cudaError_t err;
   const int n_sm = sm_count(&err);
   if (err != cudaSuccess) return err;
@@ -539,12 +559,12 @@ cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, cons
   const int nslot = tc::slots_per_thread(g.K, g.H);
   const int smem = tc::smem_plan(tc_cg, g.Kp, g.SL).total;
   switch (tc_cg) {
-    case 16: return launch_cg<16>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream);
-    case 32: return launch_cg<32>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream);
-    case 48: return launch_cg<48>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream);
-    case 64: return launch_cg<64>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream);
-    case 80: return launch_cg<80>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream);
-    case 96: return launch_cg<96>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream);
+    case 16: return launch_cg<16>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
+    case 32: return launch_cg<32>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
+    case 48: return launch_cg<48>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
+    case 64: return launch_cg<64>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
+    case 80: return launch_cg<80>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
+    case 96: return launch_cg<96>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
     default: return cudaErrorNotSupported;
   }
 }

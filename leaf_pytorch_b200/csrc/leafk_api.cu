@@ -20,7 +20,8 @@ constexpr int F32_TILE = 512;
 // k1_tc.cu
 bool k1_tc_supported(const Geom& g, const char** why);
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm,
-                         float* ppart, int tc_cg, int tc_groups, cudaStream_t stream);
+                         float* ppart, int tc_cg, int tc_groups, cudaStream_t stream, const int* ready,
+                         int clips_per_flag);
 constexpr int TC_TILE = 1024;
 // k2_pcen.cu
 cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cudaStream_t stream);
@@ -114,6 +115,7 @@ static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace
   const int sl32 = (F32_TILE + g.K - 2) / g.H + 1, sltc = (TC_TILE + g.K - 2) / g.H + 1;
   size_t a = (size_t)max_tiles_fp32 * sl32, b = (size_t)max_tiles_tc * sltc;
   off += align256(sizeof(float) * (size_t)g.B * g.F * (a > b ? a : b));
+  w->off_flags = off; off += 256;                      // 64 slice-ready flags (leafk_forward_host)
   w->total = off;
 }
 
@@ -155,12 +157,14 @@ size_t leafk_workspace_bytes(const leafk_config* cfg, int B, int n_frames) {
   return w.total;
 }
 
-int leafk_forward_window(const leafk_config* cfg, const leafk_params* prm, const float* x_win, int B,
-                         long long ldx, long long T_total, long long t_off, int T_win, int n_begin,
-                         int n_count, const float* ema_state_in, float* ema_state_out, float* out,
-                         float* saved_p, long long ldo_b, long long ldo_f, void* workspace,
-                         size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+// Shared implementation.  flag_slices > 0: the tensor-core kernel waits per clip on slice-ready flags (in the
+// workspace, `clips_per_flag` clips each) that the caller sets with stream-ordered writes.
+static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const float* x_win, int B,
+                        long long ldx, long long T_total, long long t_off, int T_win, int n_begin,
+                        int n_count, const float* ema_state_in, float* ema_state_out, float* out,
+                        float* saved_p, long long ldo_b, long long ldo_f, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream, int clips_per_flag, int** flags_out,
+                        int* algo_out) {
   if (!cfg || !prm || !x_win || !out || !workspace) return fail(LEAFK_EINVAL, "null pointer argument");
   if (!prm->kernel || !prm->pool_w) return fail(LEAFK_EINVAL, "null Gabor / pooling parameter");
   if (cfg->compression && (!prm->alpha || !prm->delta || !prm->root || !prm->ema_w))
@@ -196,8 +200,12 @@ int leafk_forward_window(const leafk_config* cfg, const leafk_params* prm, const
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0 launch: %s", cudaGetErrorString(err));
   prof_mark(1, stream);
+  int* flags = (int*)(base + w.off_flags);
+  if (flags_out) *flags_out = flags;
+  if (algo_out) *algo_out = algo;
   if (algo == LEAFK_ALGO_TC)
-    err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, stream);
+    err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, stream, clips_per_flag > 0 ? flags : nullptr,
+                       clips_per_flag);
   else
     err = launch_k1_fp32(g, x_win, w32, g32, ppart, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k1 launch: %s", cudaGetErrorString(err));
@@ -214,6 +222,53 @@ int leafk_forward_window(const leafk_config* cfg, const leafk_params* prm, const
   return LEAFK_OK;
 }
 
+// workspace offset of the flags without running anything (for leafk_forward_host)
+static int flags_location(const leafk_config* cfg, int B, int T, void* workspace, size_t workspace_bytes, int** flags,
+                          int* algo) {
+  const int N = leafk_num_frames(T, cfg->K, cfg->H);
+  Geom g;
+  int rc = make_geom(cfg, B, T, T, 0, T, 0, N, TC_TILE, &g);
+  if (rc) return rc;
+  *algo = pick_algo(cfg, g);
+  if (*algo == LEAFK_ALGO_FP32) {
+    rc = make_geom(cfg, B, T, T, 0, T, 0, N, F32_TILE, &g);
+    if (rc) return rc;
+  }
+  Workspace w;
+  int cg, ng;
+  carve(g, *algo == LEAFK_ALGO_FP32 ? g.n_tiles : 0, *algo == LEAFK_ALGO_TC ? g.n_tiles : 0, &w, &cg, &ng);
+  if (w.total > workspace_bytes) return fail(LEAFK_EWORKSPACE, "workspace %zu bytes < %zu needed", workspace_bytes, w.total);
+  *flags = (int*)((uint8_t*)workspace + w.off_flags);
+  return LEAFK_OK;
+}
+
+typedef int (*StreamWriteValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static StreamWriteValue32Fn stream_write_value32() {
+  static StreamWriteValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (StreamWriteValue32Fn)p;
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+int leafk_forward_window(const leafk_config* cfg, const leafk_params* prm, const float* x_win, int B,
+                         long long ldx, long long T_total, long long t_off, int T_win, int n_begin,
+                         int n_count, const float* ema_state_in, float* ema_state_out, float* out,
+                         float* saved_p, long long ldo_b, long long ldo_f, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return forward_impl(cfg, prm, x_win, B, ldx, T_total, t_off, T_win, n_begin, n_count, ema_state_in,
+                      ema_state_out, out, saved_p, ldo_b, ldo_f, workspace, workspace_bytes, (cudaStream_t)stream, 0,
+                      nullptr, nullptr);
+}
+
 int leafk_forward(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
                   float* out, float* saved_p, void* workspace, size_t workspace_bytes, void* stream) {
   if (!cfg) return fail(LEAFK_EINVAL, "null config");
@@ -223,18 +278,10 @@ int leafk_forward(const leafk_config* cfg, const leafk_params* prm, const float*
                               (long long)cfg->F * N, N, workspace, workspace_bytes, stream);
 }
 
-int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B, int T,
-                       float* out_host, int n_slices, float* dev_x, float* dev_out, void* workspace,
-                       size_t workspace_bytes, void* stream_, void* copy_stream_) {
-  if (!cfg || !x_host || !out_host || !dev_x || !dev_out) return fail(LEAFK_EINVAL, "null pointer argument");
-  cudaStream_t stream = (cudaStream_t)stream_, cstream = (cudaStream_t)copy_stream_;
-  const int N = leafk_num_frames(T, cfg->K, cfg->H);
-  if (N < 1 || B < 1) return fail(LEAFK_EINVAL, "bad B/T");
-  if (n_slices < 1) n_slices = 1;
-  if (n_slices > B) n_slices = B;
-  if (n_slices > 16) n_slices = 16;
-  // Slice i: H2D on copy_stream -> event -> kernels on stream -> event -> D2H on copy_stream.
-  // The workspace is shared by all slices (kernels of consecutive slices serialise on `stream`).
+// Sliced fallback of leafk_forward_host: slice i = H2D on copy_stream -> kernels on stream -> D2H.
+static int forward_host_sliced(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B, int T,
+                               int N, float* out_host, int n_slices, float* dev_x, float* dev_out, void* workspace,
+                               size_t workspace_bytes, cudaStream_t stream, cudaStream_t cstream) {
   cudaEvent_t up[16], done[16];
   int rc = LEAFK_OK;
   const bool two = (cstream != stream);
@@ -268,6 +315,53 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
   }
   for (int i = 0; i < made; ++i) { cudaEventDestroy(up[i]); cudaEventDestroy(done[i]); }
   return rc;
+}
+
+int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B, int T,
+                       float* out_host, int n_slices, float* dev_x, float* dev_out, void* workspace,
+                       size_t workspace_bytes, void* stream_, void* copy_stream_) {
+  if (!cfg || !prm || !x_host || !out_host || !dev_x || !dev_out || !workspace)
+    return fail(LEAFK_EINVAL, "null pointer argument");
+  cudaStream_t stream = (cudaStream_t)stream_, cstream = (cudaStream_t)copy_stream_;
+  const int N = leafk_num_frames(T, cfg->K, cfg->H);
+  if (N < 1 || B < 1) return fail(LEAFK_EINVAL, "bad B/T");
+  if (n_slices < 1) n_slices = 1;
+  if (n_slices > B) n_slices = B;
+  if (n_slices > 64) n_slices = 64;
+  int* flags = nullptr;
+  int algo = 0;
+  int rc = flags_location(cfg, B, T, workspace, workspace_bytes, &flags, &algo);
+  if (rc) return rc;
+  StreamWriteValue32Fn write32 = stream_write_value32();
+  if (algo != LEAFK_ALGO_TC || cstream == stream || write32 == nullptr || n_slices == 1)
+    return forward_host_sliced(cfg, prm, x_host, B, T, N, out_host, n_slices > 16 ? 16 : n_slices, dev_x, dev_out,
+                               workspace, workspace_bytes, stream, cstream);
+
+  // Pipelined path: ONE persistent launch of the tensor-core kernel over the whole batch; its producers wait
+  // per clip on slice-ready flags that follow each slice of the H2D copy in copy_stream order.
+  const int clips_per_flag = (B + n_slices - 1) / n_slices;
+  const int n_flags = (B + clips_per_flag - 1) / clips_per_flag;
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * 64, stream);
+  if (e != cudaSuccess) return fail(LEAFK_ECUDA, "flag reset: %s", cudaGetErrorString(e));
+  cudaEvent_t reset_done;
+  cudaEventCreateWithFlags(&reset_done, cudaEventDisableTiming);
+  cudaEventRecord(reset_done, stream);
+  cudaStreamWaitEvent(cstream, reset_done, 0);         // flag writes must not be overtaken by the reset
+  cudaEventDestroy(reset_done);
+  for (int s = 0; s < n_flags; ++s) {
+    const int b0 = s * clips_per_flag, b1 = (b0 + clips_per_flag < B) ? b0 + clips_per_flag : B;
+    e = cudaMemcpyAsync(dev_x + (size_t)b0 * T, x_host + (size_t)b0 * T, sizeof(float) * (size_t)(b1 - b0) * T,
+                        cudaMemcpyHostToDevice, cstream);
+    if (e != cudaSuccess) return fail(LEAFK_ECUDA, "H2D: %s", cudaGetErrorString(e));
+    if (write32(cstream, (unsigned long long)(uintptr_t)(flags + s), 1u, 0u) != 0)
+      return fail(LEAFK_ECUDA, "cuStreamWriteValue32 failed");
+  }
+  rc = forward_impl(cfg, prm, dev_x, B, T, T, 0, T, 0, N, nullptr, nullptr, dev_out, nullptr, (long long)cfg->F * N, N,
+                    workspace, workspace_bytes, stream, clips_per_flag, nullptr, nullptr);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(out_host, dev_out, sizeof(float) * (size_t)B * cfg->F * N, cudaMemcpyDeviceToHost, stream);
+  if (e != cudaSuccess) return fail(LEAFK_ECUDA, "D2H: %s", cudaGetErrorString(e));
+  return LEAFK_OK;
 }
 
 size_t leafk_backward_workspace_bytes(const leafk_config* cfg, int B, int T) { return bwd_workspace_bytes(cfg, B, T); }

@@ -191,7 +191,7 @@ class Leaf(nn.Module):
         return LF.leaf_forward(self.spec, x, *self._param_tuple())
 
     def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
-                     n_slices: int = 4) -> torch.Tensor:
+                     n_slices: int = 8) -> torch.Tensor:
         """Inference on host buffers: pinned (B,1,T) in -> pinned (B,F,N) out, H2D / kernels / D2H
         pipelined over batch slices inside the library (leafk_forward_host).  No autograd."""
         prm = [None if p is None else p.detach() for p in self._param_tuple()]

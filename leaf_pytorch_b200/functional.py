@@ -208,9 +208,11 @@ _host_cache = {}
 
 
 def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, alpha, delta, root, ema_w,
-                 out_host: Optional[torch.Tensor] = None, n_slices: int = 4, device=None) -> torch.Tensor:
-    """End-to-end call on HOST buffers through leafk_forward_host: the batch is cut into
-    ``n_slices`` pieces whose H2D copy, kernels and D2H copy overlap on two streams.  ``x_host``
+                 out_host: Optional[torch.Tensor] = None, n_slices: int = 8, device=None) -> torch.Tensor:
+    """End-to-end call on HOST buffers through leafk_forward_host: the H2D copy is issued in
+    ``n_slices`` pieces on a side stream, each followed by a stream-ordered flag write, and ONE
+    persistent launch of the tensor-core kernel consumes clips as their slice lands (the FP32 kernel
+    falls back to per-slice launches).  ``x_host``
     (B,1,T) float32 CPU (pinned for full speed); returns ``out_host`` (B,F,N) pinned CPU.  The call
     synchronises the compute stream before returning (the result is on the host)."""
     L = N.lib()

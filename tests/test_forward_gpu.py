@@ -119,3 +119,52 @@ def test_cpu_tensor_fails_loudly():
     fe = L.Leaf()
     with pytest.raises(L.LeafNativeError):
         fe(torch.zeros(1, 1, 1600))
+
+
+@pytest.mark.parametrize("n_slices", [1, 3, 8])
+def test_forward_host_pipelined_equals_device_forward(n_slices):
+    """leafk_forward_host (pinned host in/out; one persistent launch gated by per-slice ready flags that follow
+    the H2D copies) must give exactly what the device-resident forward gives."""
+    case, x, prm, z = load_golden("cfg1_default")
+    fe = build(case, prm, "auto")
+    xb = torch.cat([x, x.flip(0), 0.5 * x], dim=0)           # 12 clips
+    with torch.no_grad():
+        want = fe(xb.cuda()).cpu()
+    xh = xb.pin_memory()
+    for _ in range(3):                                       # buffers are reused across calls
+        got = fe.forward_host(xh, n_slices=n_slices)
+        assert torch.equal(got, want)
+    assert_close(got[:4].numpy(), z["out"], "forward_host")
+
+
+def test_forward_host_fp32_algo_uses_sliced_path():
+    case, x, prm, z = load_golden("cfg1_default")
+    fe = build(case, prm, "fp32")
+    got = fe.forward_host(x.pin_memory(), n_slices=2)
+    assert_close(got.numpy(), z["out"], "forward_host/fp32")
+
+
+def test_exact_power_of_two_scaling_of_energies():
+    """Size-independent property at BASELINE configs[1] size (256 x 1 s): with PCEN off and zero bias the pooled
+    energies are homogeneous of degree 2, and because the kernel's per-tile scaling is an exact power of two,
+    out(4x) == 16*out(x) bit for bit."""
+    import leaf_pytorch_b200 as L
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(256, 1, 16000, generator=g).clamp_(-4, 4) / 4).cuda()
+    fe = L.Leaf(pcen_compression=False).cuda()
+    with torch.no_grad():
+        fe._pooling._bias.zero_()
+        a = fe(x)
+        b = fe(4.0 * x)
+    assert torch.equal(b, 16.0 * a)
+    assert float(a.min()) >= 1e-5
+
+
+def test_batch_permutation_equivariance_full_size():
+    import leaf_pytorch_b200 as L
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(256, 1, 16000, generator=g).clamp_(-4, 4) / 4).cuda()
+    perm = torch.randperm(256, generator=g).cuda()
+    fe = L.Leaf().cuda()
+    with torch.no_grad():
+        assert torch.equal(fe(x)[perm], fe(x[perm].contiguous()))
