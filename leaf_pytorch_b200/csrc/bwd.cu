@@ -335,6 +335,9 @@ int bwd_run(const leafk_config* cfg, const leafk_params* prm, const float* x, in
   err = cudaGetLastError();
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0_bwd launch: %s", cudaGetErrorString(err));
 
+  // rows of bpart that no CTA owns (uneven pair split, fewer unit pairs than SM pairs) must read as zero
+  err = cudaMemsetAsync(bpart, 0, sizeof(float) * (size_t)pl.max_ctas * pl.Fpad * 4, stream);
+  if (err != cudaSuccess) return fail(LEAFK_ECUDA, "bpart reset: %s", cudaGetErrorString(err));
   int ctas_per_group = 0;
   err = launch_k1_tc_bwd(g, x, w16b, pl.FB, pl.n_groups, dpT, bprm, bpart, &ctas_per_group, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k1_tc_bwd launch: %s", cudaGetErrorString(err));

@@ -41,8 +41,10 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
         if (c < C2p) w32[(size_t)k * C2p + c] = 0.f;
         if (w16 != nullptr && c < tc_cg * tc_groups) {
           uint8_t* gb = w16 + (size_t)(c / tc_cg) * grp_bytes;
-          *reinterpret_cast<__half*>(gb + tc::b_offset(tc_cg, c % tc_cg, k)) = __float2half_rn(0.f);
-          *reinterpret_cast<__half*>(gb + tc::b_offset(tc_cg, tc_cg + c % tc_cg, k)) = __float2half_rn(0.f);
+          const __half z = __float2half_rn(0.f);
+          *reinterpret_cast<__half*>(gb + tc::g_hi_main(tc_cg, Kp, c % tc_cg, k)) = z;
+          *reinterpret_cast<__half*>(gb + tc::g_lo_main(tc_cg, Kp, c % tc_cg, k)) = z;
+          *reinterpret_cast<__half*>(gb + tc::g_hi_corr(tc_cg, Kp, c % tc_cg, k)) = z;
         }
       }
     }
@@ -91,8 +93,8 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
     w32[(size_t)k * C2p + 2 * f] = wr;
     w32[(size_t)k * C2p + 2 * f + 1] = wi;
     if (w16 != nullptr) {
-      // hi/lo fp16 split of the scaled taps; B-operand rows of the channel's group:
-      // [0,CG) = hi halves, [CG,2CG) = lo halves (k1_tc_layout.cuh)
+      // hi/lo fp16 split of the scaled taps, stored in the CTA-pair regions of the channel's group
+      // (k1_tc_layout.cuh): hi -> R1 of CTA0 and R2 of CTA (c / (CG/2)); lo -> R1 of CTA1
       const float sc[2] = {ldexpf(wr, wshift), ldexpf(wi, wshift)};
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
@@ -100,8 +102,9 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
         uint8_t* gb = w16 + (size_t)(c / tc_cg) * grp_bytes;
         const __half hi = __float2half_rn(sc[q]);
         const __half lo = __float2half_rn(sc[q] - __half2float(hi));
-        *reinterpret_cast<__half*>(gb + tc::b_offset(tc_cg, c % tc_cg, k)) = hi;
-        *reinterpret_cast<__half*>(gb + tc::b_offset(tc_cg, tc_cg + c % tc_cg, k)) = lo;
+        *reinterpret_cast<__half*>(gb + tc::g_hi_main(tc_cg, Kp, c % tc_cg, k)) = hi;
+        *reinterpret_cast<__half*>(gb + tc::g_lo_main(tc_cg, Kp, c % tc_cg, k)) = lo;
+        *reinterpret_cast<__half*>(gb + tc::g_hi_corr(tc_cg, Kp, c % tc_cg, k)) = hi;
       }
     }
   }
@@ -126,8 +129,10 @@ k0_banks_bwd_kernel(const float* __restrict__ kernel, const float* __restrict__ 
       for (int kind = 0; kind < 3; ++kind)
         for (int ri = 0; ri < 2; ++ri) {
           const int c = tc::bwd_channel(FB, fl, kind, ri);
-          *reinterpret_cast<__half*>(gb + tc::b_offset(CG, c, k)) = __float2half_rn(0.f);
-          *reinterpret_cast<__half*>(gb + tc::b_offset(CG, CG + c, k)) = __float2half_rn(0.f);
+          const __half z = __float2half_rn(0.f);
+          *reinterpret_cast<__half*>(gb + tc::g_hi_main(CG, Kp, c, k)) = z;
+          *reinterpret_cast<__half*>(gb + tc::g_lo_main(CG, Kp, c, k)) = z;
+          *reinterpret_cast<__half*>(gb + tc::g_hi_corr(CG, Kp, c, k)) = z;
         }
     if (tid == 0) {
       float* bp = bprm + (size_t)f * 8;
@@ -196,8 +201,9 @@ k0_banks_bwd_kernel(const float* __restrict__ kernel, const float* __restrict__ 
         const __half hi = __float2half_rn(sc);
         const __half lo = __float2half_rn(sc - __half2float(hi));
         const int c = tc::bwd_channel(FB, fl, kind, ri);
-        *reinterpret_cast<__half*>(gb + tc::b_offset(CG, c, k)) = hi;
-        *reinterpret_cast<__half*>(gb + tc::b_offset(CG, CG + c, k)) = lo;
+        *reinterpret_cast<__half*>(gb + tc::g_hi_main(CG, Kp, c, k)) = hi;
+        *reinterpret_cast<__half*>(gb + tc::g_lo_main(CG, Kp, c, k)) = lo;
+        *reinterpret_cast<__half*>(gb + tc::g_hi_corr(CG, Kp, c, k)) = hi;
       }
   }
 }

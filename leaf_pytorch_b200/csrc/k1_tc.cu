@@ -86,7 +86,7 @@ __device__ __forceinline__ void build_copy(tc::Misc* misc, const uint4* sth4, co
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&misc->a_full[P]);
+  if (lane == 0) mbar_arrive_rank0(&misc->a_full[P]);      // the MMA issuer lives in rank 0 of the pair
 }
 
 // Extra arguments of the backward variant (MODE 1): the epilogue turns the three correlations
@@ -107,8 +107,11 @@ struct TcBwdArgs {
   int Fpad;             // n_groups * FB
 };
 
-template <int CG, int NSLOT, int MODE>
-__global__ void __launch_bounds__(tc::NTHREADS, 1)
+// KS > 0: number of k-steps known at compile time (26 for the default 401-tap window): the MMA issue loop is
+// fully unrolled with immediate descriptor offsets -- with a runtime trip count the per-iteration descriptor
+// arithmetic made the single issuing lane the bottleneck (149 cycles per k-step measured vs 124 issued tight).
+template <int CG, int NSLOT, int MODE, int KS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1)
 k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restrict__ w16,
              const float* __restrict__ cprm, float* __restrict__ ppart, int n_groups, const TcBwdArgs ba,
              const TcReady rdy) {
@@ -116,8 +119,8 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   constexpr int NB = 2 * CG;                 // accumulator columns per stage (hi | lo products)
   constexpr int NST = (512 / NB) > 4 ? 4 : (512 / NB);
   constexpr int FPT = CG / 4;                // filters per epilogue thread
-  constexpr uint32_t IDESC_MAIN = idesc_f16(128, NB);
-  constexpr uint32_t IDESC_CORR = idesc_f16(128, CG);
+  constexpr uint32_t IDESC_MAIN = idesc_f16(256, NB);   // M = 256: 128 rows from each CTA of the pair
+  constexpr uint32_t IDESC_CORR = idesc_f16(256, CG);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const SmemPlan sp = smem_plan(CG, g.Kp, g.SL, MODE);
@@ -130,28 +133,40 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   Misc* misc = reinterpret_cast<Misc*>(smem + sp.off_misc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int grp = blockIdx.x % n_groups;
-  const int cta_in_grp = blockIdx.x / n_groups;
-  const int ctas_per_grp = gridDim.x / n_groups;
+  // CTA pair = cluster of 2 (same TPC).  Both CTAs serve the same channel group; the pair takes two units
+  // (tiles) per iteration, rank r the unit 2*pair_unit + r.  Rank 0 issues the MMAs for both.
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int grp = pair % n_groups;
+  const int pair_in_grp = pair / n_groups;
+  const int pairs_in_grp = (n_pairs - grp + n_groups - 1) / n_groups;
   const long long n_units = (long long)g.B * g.n_tiles;
+  const long long n_pair_units = (n_units + 1) / 2;
+  const int cta_in_grp = pair_in_grp * 2 + (int)rank;    // row of the backward partial buffer
   const int ksteps = g.Kp / KSTEP;
 
   // ---- one-time setup ---------------------------------------------------------------------------
   {
-    const size_t gbytes = b_group_bytes(CG, g.Kp);
-    const uint4* src = reinterpret_cast<const uint4*>(w16 + (size_t)grp * gbytes);
+    // this CTA's bank regions: R1 (main MMA) then R2 (corr MMA), from the group's global image
+    const uint8_t* gimg = w16 + (size_t)grp * b_group_bytes(CG, g.Kp);
+    const size_t r1 = r1_bytes(CG, g.Kp), r2 = r2_bytes(CG, g.Kp);
+    const uint4* src1 = reinterpret_cast<const uint4*>(gimg + rank * r1);
+    const uint4* src2 = reinterpret_cast<const uint4*>(gimg + 2 * r1 + rank * r2);
     uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = tid; i < (int)(gbytes / 16); i += NTHREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < (int)(r1 / 16); i += NTHREADS) dst[i] = __ldg(src1 + i);
+    for (int i = tid; i < (int)(r2 / 16); i += NTHREADS) dst[r1 / 16 + i] = __ldg(src2 + i);
   }
   if (tid == 0) {
-    for (int p = 0; p < NPHASE; ++p) { mbar_init(&misc->a_full[p], PROD_WARPS); mbar_init(&misc->a_empty[p], 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&misc->acc_full[s], 1); mbar_init(&misc->acc_empty[s], EPI_WARPS); }
+    // a_full / acc_empty live on rank 0 and collect arrivals from BOTH CTAs; a_empty / acc_full are local
+    // and are signalled in both CTAs by the multicast tcgen05.commit of rank 0.
+    for (int p = 0; p < NPHASE; ++p) { mbar_init(&misc->a_full[p], 2 * PROD_WARPS); mbar_init(&misc->a_empty[p], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&misc->acc_full[s], 1); mbar_init(&misc->acc_empty[s], 2 * EPI_WARPS); }
     mbar_init_fence();
   }
-  if (warp == MMA_WARP) tmem_alloc<512>(&misc->tmem_base);
+  if (warp == MMA_WARP) tmem_alloc_pair<512>(&misc->tmem_base);
   fence_proxy_async_smem();                  // bank written with generic stores, read by the MMA (async proxy)
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();                        // barriers + TMEM of both CTAs ready before any remote arrive / MMA
   tc_fence_after();
   const uint32_t tmem = misc->tmem_base;
 
@@ -160,11 +175,13 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
     const int ptid = tid - PROD_WARP0 * 32;
     const int nchunk = sp.CL / 8;            // 16-byte chunks per copy
     int it = 0;
-    for (long long u = cta_in_grp; u < n_units; u += ctas_per_grp, ++it) {
-      const int b = (int)(u / g.n_tiles), tile = (int)(u % g.n_tiles);
+    for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
+      const long long u = 2 * pu + rank;
+      const bool valid = u < n_units;                // odd unit count: the last pair's rank 1 runs on zeros
+      const int b = valid ? (int)(u / g.n_tiles) : 0, tile = valid ? (int)(u % g.n_tiles) : 0;
       const long long ts = g.te_lo + (long long)tile * TILE;
       const float* xrow = x + (size_t)b * g.ldx;
-      if (rdy.ready != nullptr && ptid == 0) {       // clip b still in flight over PCIe?
+      if (valid && rdy.ready != nullptr && ptid == 0) {       // clip b still in flight over PCIe?
         const int* flag = rdy.ready + b / rdy.clips_per_flag;
         int v;
         unsigned spins = 0;
@@ -178,7 +195,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       for (int i = ptid; i < sp.LX; i += PROD_THREADS) {
         const long long a = ts - g.padL + i, wi = a - g.t_off;
         float v = 0.f;
-        if (a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win) v = xrow[wi];   // coherent load: may have just landed
+        if (valid && a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win) v = xrow[wi];   // coherent load: may have just landed
         s_st32[i] = v;
         mx = fmaxf(mx, fabsf(v));
       }
@@ -215,34 +232,44 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       build_copy<7>(misc, sth4, stl4, s_acopy, sp.acb, nchunk, ptid, lane, it);
     }
   } else if (warp == MMA_WARP) {
-    // =========================================== MMA ISSUER =====================================
-    const bool leader = elect_one();
-    const uint32_t a_base = smem_u32(s_acopy), w_base = smem_u32(s_w);
-    const uint64_t b_desc0 = smem_desc(w_base, NB * 16, 128);
-    const uint64_t b_step = (uint64_t)((NB * 32) >> 4);
-    int it = 0;
-    for (long long u = cta_in_grp; u < n_units; u += ctas_per_grp, ++it) {
+    // =========================================== MMA ISSUER (rank 0 only) =======================
+    if (rank == 0) {
+      const bool leader = elect_one();
+      const uint32_t a_base = smem_u32(s_acopy), w_base = smem_u32(s_w);
+      const uint64_t b1_desc0 = smem_desc(w_base, CG * 16, 128);                               // R1: CG rows per CTA
+      const uint64_t b2_desc0 = smem_desc(w_base + (uint32_t)r1_bytes(CG, g.Kp), (CG / 2) * 16, 128);  // R2: CG/2 rows
+      const uint64_t b1_step = (uint64_t)((CG * 32) >> 4), b2_step = (uint64_t)(((CG / 2) * 32) >> 4);
+      int it = 0;
+      for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
 #pragma unroll 1
-      for (int p = 0; p < NPHASE; ++p) {
-        const int gp = it * NPHASE + p;
-        const int st = gp % NST;
-        mbar_wait(&misc->a_full[p], (uint32_t)(it & 1));
-        mbar_wait(&misc->acc_empty[st], (uint32_t)(((gp / NST) & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t d = tmem + (uint32_t)(st * NB);
-        const uint64_t a_hi = smem_desc(a_base + (uint32_t)((2 * p) * sp.acb), 16, 128);
-        const uint64_t a_lo = smem_desc(a_base + (uint32_t)((2 * p + 1) * sp.acb), 16, 128);
-        if (leader) {
+        for (int p = 0; p < NPHASE; ++p) {
+          const int gp = it * NPHASE + p;
+          const int st = gp % NST;
+          mbar_wait_cluster(&misc->a_full[p], (uint32_t)(it & 1));
+          mbar_wait_cluster(&misc->acc_empty[st], (uint32_t)(((gp / NST) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t d = tmem + (uint32_t)(st * NB);
+          const uint64_t a_hi = smem_desc(a_base + (uint32_t)((2 * p) * sp.acb), 16, 128);
+          const uint64_t a_lo = smem_desc(a_base + (uint32_t)((2 * p + 1) * sp.acb), 16, 128);
+          if (leader) {
+            if constexpr (KS > 0) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)(ks * ((CG * 32) >> 4)), IDESC_MAIN, ks > 0);
+                mma_f16_ss_pair(d, a_lo + (uint64_t)(2 * ks), b2_desc0 + (uint64_t)(ks * (((CG / 2) * 32) >> 4)), IDESC_CORR, 1);
+              }
+            } else {
 #pragma unroll 2
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t bd = b_desc0 + (uint64_t)ks * b_step;
-            mma_f16_ss(d, a_hi + (uint64_t)(2 * ks), bd, IDESC_MAIN, ks > 0);
-            mma_f16_ss(d, a_lo + (uint64_t)(2 * ks), bd, IDESC_CORR, 1);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)ks * b1_step, IDESC_MAIN, ks > 0);
+                mma_f16_ss_pair(d, a_lo + (uint64_t)(2 * ks), b2_desc0 + (uint64_t)ks * b2_step, IDESC_CORR, 1);
+              }
+            }
+            mma_commit_pair(&misc->a_empty[p]);
+            mma_commit_pair(&misc->acc_full[st]);
           }
-          mma_commit(&misc->a_empty[p]);
-          mma_commit(&misc->acc_full[st]);
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if constexpr (MODE == 0) {
@@ -257,10 +284,12 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
     const float centre = 0.5f * (float)(g.K - 1);
     const int n_last = g.n_begin + g.n_count - 1;
     int it = 0;
-    for (long long u = cta_in_grp; u < n_units; u += ctas_per_grp, ++it) {
-      const int b = (int)(u / g.n_tiles), tile = (int)(u % g.n_tiles);
+    for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
+      const long long u = 2 * pu + rank;
+      const bool valid = u < n_units;
+      const int b = valid ? (int)(u / g.n_tiles) : 0, tile = valid ? (int)(u % g.n_tiles) : 0;
       const long long ts = g.te_lo + (long long)tile * TILE;
-      const long long te = (ts + TILE < g.te_hi) ? ts + TILE : g.te_hi;
+      const long long te = !valid ? ts : ((ts + TILE < g.te_hi) ? ts + TILE : g.te_hi);   // invalid unit: all rows masked
       const int n_first = first_frame_of(g, ts);
       const long long tb = ts + 8 * m;                  // this row's 8 samples: tb .. tb+7
       const int nb = first_frame_of(g, tb);
@@ -302,7 +331,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&misc->acc_empty[st]);
+        if (lane == 0) mbar_arrive_rank0(&misc->acc_empty[st]);
       }
 
       // ---- reduce over the rows of this warp: per-frame sums -> s_pw[buf][e][slot][fi] ----------
@@ -335,7 +364,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         const int fl = idx / g.SL, slot = idx % g.SL;       // (filter, slot) layout, slot fastest
         const int h2 = fl / FPT, fi = fl % FPT;
         const int f = grp * (CG / 2) + fl;
-        if (f < g.F) {
+        if (valid && f < g.F) {
           float s = 0.f;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) s += pw_buf[((size_t)(h2 * 4 + qq) * g.SL + slot) * FPT + fi];
@@ -365,10 +394,12 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
     const float centre = 0.5f * (float)(g.K - 1);
     const int n_last = g.n_begin + g.n_count - 1;
     int it = 0;
-    for (long long u = cta_in_grp; u < n_units; u += ctas_per_grp, ++it) {
-      const int b = (int)(u / g.n_tiles), tile = (int)(u % g.n_tiles);
+    for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
+      const long long u = 2 * pu + rank;
+      const bool valid = u < n_units;
+      const int b = valid ? (int)(u / g.n_tiles) : 0, tile = valid ? (int)(u % g.n_tiles) : 0;
       const long long ts = g.te_lo + (long long)tile * TILE;
-      const long long te = (ts + TILE < g.te_hi) ? ts + TILE : g.te_hi;
+      const long long te = !valid ? ts : ((ts + TILE < g.te_hi) ? ts + TILE : g.te_hi);   // invalid unit: all rows masked
       const long long tb = ts + 8 * m;
       const int nb = first_frame_of(g, tb);
       float dpv[NSLOT][FPB];
@@ -434,7 +465,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&misc->acc_empty[st]);
+        if (lane == 0) mbar_arrive_rank0(&misc->acc_empty[st]);
       }
     }
     // ---- CTA reduction of the 3*FPB sums per thread -> one partial row per filter ----------------
@@ -463,8 +494,8 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
 
   // ---- teardown -----------------------------------------------------------------------------------
   tc_fence_before();
-  __syncthreads();
-  if (warp == tc::MMA_WARP) tmem_dealloc<512>(tmem);
+  cluster_sync_all();                        // nobody may still signal a peer barrier / use TMEM
+  if (warp == tc::MMA_WARP) tmem_dealloc_pair<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -480,25 +511,41 @@ bool k1_tc_supported(const Geom& g, const char** why) {
   return true;
 }
 
+template <int CG, int NSLOT, int KS>
+static cudaError_t launch_inst_ks(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
+                                  int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy) {
+  cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  TcBwdArgs none{nullptr, nullptr, nullptr, 0};
+  k1_tc_kernel<CG, NSLOT, 0, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups, none, rdy);
+  return cudaGetLastError();
+}
 template <int CG, int NSLOT>
 static cudaError_t launch_inst(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
                                int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy) {
-  cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (err != cudaSuccess) return err;
-  TcBwdArgs none{nullptr, nullptr, nullptr, 0};
-  k1_tc_kernel<CG, NSLOT, 0><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups, none, rdy);
-  return cudaGetLastError();
+  if constexpr (NSLOT == 3 && (CG == 80 || CG == 64)) {      // the shipped configs (F=40/80, F=64) at 401 taps
+    if (g.Kp == 26 * tc::KSTEP) return launch_inst_ks<CG, NSLOT, 26>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy);
+  }
+  return launch_inst_ks<CG, NSLOT, 0>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy);
 }
 
+template <int CG, int NSLOT, int KS>
+static cudaError_t launch_bwd_inst_ks(const Geom& g, const float* x, const uint8_t* w16, int n_groups, int grid,
+                                      const TcBwdArgs& ba, cudaStream_t stream) {
+  const int smem = tc::smem_plan(CG, g.Kp, g.SL, 1).total;
+  cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 1, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (err != cudaSuccess) return err;
+  k1_tc_kernel<CG, NSLOT, 1, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, nullptr, nullptr, n_groups, ba,
+                                                                       TcReady{nullptr, 1});
+  return cudaGetLastError();
+}
 template <int CG, int NSLOT>
 static cudaError_t launch_bwd_inst(const Geom& g, const float* x, const uint8_t* w16, int n_groups, int grid,
                                    const TcBwdArgs& ba, cudaStream_t stream) {
-  const int smem = tc::smem_plan(CG, g.Kp, g.SL, 1).total;
-  cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (err != cudaSuccess) return err;
-  k1_tc_kernel<CG, NSLOT, 1><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, nullptr, nullptr, n_groups, ba,
-                                                                   TcReady{nullptr, 1});
-  return cudaGetLastError();
+  if constexpr (CG == 96) {
+    if (g.Kp == 26 * tc::KSTEP) return launch_bwd_inst_ks<CG, NSLOT, 26>(g, x, w16, n_groups, grid, ba, stream);
+  }
+  return launch_bwd_inst_ks<CG, NSLOT, 0>(g, x, w16, n_groups, grid, ba, stream);
 }
 
 static int sm_count(cudaError_t* err) {
@@ -523,12 +570,8 @@ cudaError_t launch_k1_tc_bwd(const Geom& g, const float* x, const uint8_t* w16b,
   cudaError_t err;
   const int n_sm = sm_count(&err);
   if (err != cudaSuccess) return err;
-  const long long n_units = (long long)g.B * g.n_tiles;
-  long long per_grp = n_sm / n_groups;
-  if (per_grp < 1) per_grp = 1;
-  if (per_grp > n_units) per_grp = n_units;
-  *ctas_per_group = (int)per_grp;
-  const int grid = (int)(per_grp * n_groups);
+  const int grid = tc::pair_grid(n_sm, n_groups, (long long)g.B * g.n_tiles);
+  *ctas_per_group = 2 * (((grid / 2) + n_groups - 1) / n_groups);   // rows of bpart (zero-filled by the caller)
   TcBwdArgs ba{dpT, bprm, bpart, n_groups * FB};
   const int nslot = tc::slots_per_thread(g.K, g.H);
   if (FB == 16 && nslot <= 3) return launch_bwd_inst<96, 3>(g, x, w16b, n_groups, grid, ba, stream);
@@ -551,11 +594,7 @@ cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, cons
   cudaError_t err;
   const int n_sm = sm_count(&err);
   if (err != cudaSuccess) return err;
-  const long long n_units = (long long)g.B * g.n_tiles;
-  long long per_grp = n_sm / tc_groups;
-  if (per_grp < 1) per_grp = 1;
-  if (per_grp > n_units) per_grp = n_units;
-  const int grid = (int)(per_grp * tc_groups);
+  const int grid = tc::pair_grid(n_sm, tc_groups, (long long)g.B * g.n_tiles);
   const int nslot = tc::slots_per_thread(g.K, g.H);
   const int smem = tc::smem_plan(tc_cg, g.Kp, g.SL).total;
   switch (tc_cg) {

@@ -3,13 +3,17 @@
 // layout), by k1_tc.cu (which copies it into shared memory unchanged) and by the host planner.
 //
 // B operand = Gabor bank of one channel group, fp16, "N x K, K-major, no swizzle" canonical
-// layout: 8x8 core matrices of 128 contiguous bytes (8 rows x 16 B).  Rows n: [0,CG) are the
-// hi halves of the group's CG channels, [CG,2CG) the lo halves (NB = 2*CG rows).  The taps are cut
-// into k-steps of 16 (one tcgen05.mma.kind::f16 each); per k-step the two 8-tap core-matrix
-// columns are stored one after the other:
-//   byte(n,k) = (k/16)*NB*32 + ((k%16)/8)*NB*16 + (n/8)*128 + (n%8)*16 + (k%8)*2
-// so for k-step s the descriptor is {start = base + s*NB*32, LBO = NB*16 (K direction),
-// SBO = 128 (N direction)}.
+// layout: 8x8 core matrices of 128 contiguous bytes (8 rows x 16 B).  The kernel runs on CTA PAIRS
+// (tcgen05 cta_group::2, M = 256): each MMA takes its 128 A rows per CTA from that CTA's own shared
+// memory and HALF of its B rows from each CTA, so per CTA the bank is stored as two regions
+//   R1 (main MMA, N = 2*CG):  CG rows  -- CTA0: hi halves of the CG channels, CTA1: lo halves
+//   R2 (corr MMA, N = CG):    CG/2 rows -- CTA0: hi halves of channels [0,CG/2), CTA1: of [CG/2,CG)
+// A region with R rows stores, per k-step of 16 taps, the two 8-tap core-matrix columns one after
+// the other:   byte(n,k) = (k/16)*R*32 + ((k%16)/8)*R*16 + (n/8)*128 + (n%8)*16 + (k%8)*2
+// so for k-step s the descriptor is {start = base + s*R*32, LBO = R*16 (K direction), SBO = 128}.
+// Global image of a group (what k0 writes, what each CTA copies): [R1 cta0 | R1 cta1 | R2 cta0 | R2 cta1].
+// (Halving the B rows each CTA feeds its tensor core is what takes the shared-memory pipe off the
+// critical path: 94 operand wavefronts per k-step instead of 124, ncu r01.)
 //
 // A operand = NOT materialised.  For phase p (0..7) a linear fp16 copy of the scaled sample window,
 // shifted by p samples, sits in shared memory: copy_p[i] = x~[ts - padL + p + i].  The descriptor
@@ -29,12 +33,21 @@ constexpr int NPHASE = 8;
 constexpr int MAX_CG = 96;           // largest channel group instantiated (NB = 192 accumulator columns)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-__host__ __device__ inline size_t b_group_bytes(int CG, int Kp) { return (size_t)Kp * (2 * CG) * 2; }
-
-__host__ __device__ inline size_t b_offset(int CG, int n, int k) {
-  const int NB = 2 * CG;
-  return (size_t)(k / 16) * NB * 32 + (size_t)((k % 16) / 8) * NB * 16 + (size_t)(n / 8) * 128 +
+__host__ __device__ inline size_t region_offset(int R, int n, int k) {
+  return (size_t)(k / 16) * R * 32 + (size_t)((k % 16) / 8) * R * 16 + (size_t)(n / 8) * 128 +
          (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
+}
+__host__ __device__ inline size_t r1_bytes(int CG, int Kp) { return (size_t)Kp * CG * 2; }
+__host__ __device__ inline size_t r2_bytes(int CG, int Kp) { return (size_t)Kp * (CG / 2) * 2; }
+__host__ __device__ inline size_t b_cta_bytes(int CG, int Kp) { return r1_bytes(CG, Kp) + r2_bytes(CG, Kp); }
+__host__ __device__ inline size_t b_group_bytes(int CG, int Kp) { return 2 * b_cta_bytes(CG, Kp); }
+
+// byte offsets, inside a group's global image, of channel c / tap k:
+__host__ __device__ inline size_t g_hi_main(int CG, int Kp, int c, int k) { return region_offset(CG, c, k); }
+__host__ __device__ inline size_t g_lo_main(int CG, int Kp, int c, int k) { return r1_bytes(CG, Kp) + region_offset(CG, c, k); }
+__host__ __device__ inline size_t g_hi_corr(int CG, int Kp, int c, int k) {
+  const int h = CG / 2;
+  return 2 * r1_bytes(CG, Kp) + (size_t)(c / h) * r2_bytes(CG, Kp) + region_offset(h, c % h, k);
 }
 
 // Byte offsets of the kernel's dynamic shared memory regions.
@@ -52,7 +65,7 @@ __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode =
   s.LX = s.CL + 8;
   s.acb = s.CL * 2;
   int off = 0;
-  s.off_w = off;      off += Kp * 2 * CG * 2;
+  s.off_w = off;      off += (int)b_cta_bytes(CG, Kp);       // R1 | R2 of this CTA
   s.off_acopy = off;  off += 16 * s.acb;
   s.off_st32 = off;   off += s.LX * 4;
   s.off_sth = off;    off += (s.LX * 2 + 15) / 16 * 16;
@@ -61,6 +74,16 @@ __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode =
   s.off_misc = (off + 15) / 16 * 16;
   s.total = s.off_misc + 512;
   return s;
+}
+
+// CTAs to launch: pairs (clusters of 2); at most one pair per two SMs, at least one pair per channel group,
+// no more pairs than there are unit pairs per group.
+inline int pair_grid(int n_sm, int n_groups, long long n_units) {
+  long long pairs = n_sm / 2;
+  const long long want = ((n_units + 1) / 2) * n_groups;
+  if (pairs > want) pairs = want;
+  if (pairs < n_groups) pairs = n_groups;
+  return (int)(2 * pairs);
 }
 
 // slots (frames) one thread's 8 consecutive samples can touch
