@@ -5,7 +5,7 @@
 //            ExponentialMovingAverage.forward         reference postprocessing.py:13-28
 //            PCENLayer.forward                        reference postprocessing.py:62-69
 // The reference runs the smoother as a Python loop over frames (5 tiny ops per frame); here it is
-// a warp scan over affine maps M -> (1-w) M + w p, 32 frames per step, with the state carried in
+// a warp scan over affine maps M -> (1-w) M + w p, 4 x 32 frames per step, with the state carried in
 // a register between steps (and in/out of the kernel for chunked long-form audio).
 //
 // One warp = one (clip, filter) row; lane = frame within a group of 32 consecutive frames, so the
@@ -23,6 +23,11 @@ __device__ __forceinline__ int ceil_div_i(int a, int b) {     // b > 0, a may be
   return (a >= 0) ? (a + b - 1) / b : -((-a) / b);
 }
 
+// x^y for x > 0 as exp2(y*log2 x) with the accurate log2f/exp2f (no fast-math): ~1e-7 * max(1,|y log2 x|)
+// relative, a third of the instructions of powf (whose special-case handling is not needed: x = floor + M > 0;
+// a negative delta gives NaN exactly like powf / the reference).
+__device__ __forceinline__ float pow_pos(float x, float y) { return exp2f(y * log2f(x)); }
+
 __global__ void __launch_bounds__(K2_WARPS * 32)
 k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, int tl_shift) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -38,7 +43,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
       alpha = fminf(__ldg(a.alpha + f), 1.0f);                 // postprocessing.py:63
       q = 1.0f / fmaxf(__ldg(a.root + f), 1.0f);               // postprocessing.py:64-65
       delta = __ldg(a.delta + f);
-      dq = powf(delta, q);
+      dq = pow_pos(delta, q);
     }
     const float om = 1.0f - w;
     const float bias = a.pool_b ? __ldg(a.pool_b + f) : 0.f;
@@ -52,45 +57,64 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
     float* orow = a.out + (size_t)b * a.ldo_b + (size_t)f * a.ldo_f;
     float* prow = a.saved_p ? a.saved_p + (size_t)b * a.ldo_b + (size_t)f * a.ldo_f : nullptr;
 
-    for (int n0 = g.n_begin; n0 < n_end; n0 += 32) {
-      const int n = n0 + lane;
-      const bool ok = n < n_end;
-      float p = 0.f;
-      if (ok) {
-        int wlo = n * g.H - g.padL, whi = wlo + g.K - 1;
-        if (wlo < te_lo) wlo = te_lo;
-        if (whi > te_hi - 1) whi = te_hi - 1;
-        const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
-        float s = 0.f;
-        for (int i = i0; i <= i1; ++i) {                      // <= ceil(K/TL)+1 tiles, in tile order
-          const int ts = te_lo + (i << tl_shift);
-          int nf = ceil_div_i(ts + g.padL - g.K + 1, g.H);
-          if (nf < g.n_begin) nf = g.n_begin;
-          s += __ldg(pbase + (size_t)i * g.F * g.SL + (n - nf));
+    // 128 frames per step: 4 independent groups of 32 consecutive frames (lane = frame within group), so the
+    // loads, the 4 local scans and the 4 PCEN evaluations of a step overlap; only 4 FMAs chain the carry.
+    for (int n0 = g.n_begin; n0 < n_end; n0 += 128) {
+      float p[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int n = n0 + 32 * u + lane;
+        ok[u] = n < n_end;
+        p[u] = 0.f;
+        if (ok[u]) {
+          int wlo = n * g.H - g.padL, whi = wlo + g.K - 1;
+          if (wlo < te_lo) wlo = te_lo;
+          if (whi > te_hi - 1) whi = te_hi - 1;
+          const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
+          float s = 0.f;
+          for (int i = i0; i <= i1; ++i) {                    // <= ceil(K/TL)+1 tiles, in tile order
+            const int ts = te_lo + (i << tl_shift);
+            int nf = ceil_div_i(ts + g.padL - g.K + 1, g.H);
+            if (nf < g.n_begin) nf = g.n_begin;
+            s += __ldg(pbase + (size_t)i * g.F * g.SL + (n - nf));
+          }
+          p[u] = fmaxf(s + bias, a.clamp_min);                // pooling.py:41, frontend.py:84
         }
-        p = fmaxf(s + bias, a.clamp_min);                     // pooling.py:41, frontend.py:84
       }
-      float o = p;
+      float o[4] = {p[0], p[1], p[2], p[3]};
       if (a.compression) {
         if (!have_carry) {                                    // smoother starts at the first frame
-          carry = __shfl_sync(0xffffffffu, p, 0);             // postprocessing.py:15
+          carry = __shfl_sync(0xffffffffu, p[0], 0);          // postprocessing.py:15
           have_carry = true;
         }
-        float A = ok ? om : 1.f, C = ok ? w * p : 0.f;        // M -> A*M + C   (postprocessing.py:22)
+        float A[4], C[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { A[u] = ok[u] ? om : 1.f; C[u] = ok[u] ? w * p[u] : 0.f; }   // M -> A*M + C
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          const float Ap = __shfl_up_sync(0xffffffffu, A, d), Cp = __shfl_up_sync(0xffffffffu, C, d);
-          if (lane >= d) { C = fmaf(A, Cp, C); A *= Ap; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float Ap = __shfl_up_sync(0xffffffffu, A[u], d), Cp = __shfl_up_sync(0xffffffffu, C[u], d);
+            if (lane >= d) { C[u] = fmaf(A[u], Cp, C[u]); A[u] *= Ap; }
+          }
         }
-        const float m = fmaf(A, carry, C);                    // smoother state after this lane's frame
-        carry = __shfl_sync(0xffffffffu, m, 31);
-        const float dd = a.pcen_floor + m;
-        const float u = p / powf(dd, alpha) + delta;          // postprocessing.py:66
-        o = powf(u, q) - dq;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float m = fmaf(A[u], carry, C[u]);            // smoother state after this lane's frame
+          carry = __shfl_sync(0xffffffffu, m, 31);
+          const float dd = a.pcen_floor + m;
+          const float uu = p[u] / pow_pos(dd, alpha) + delta; // postprocessing.py:66
+          o[u] = pow_pos(uu, q) - dq;
+        }
       }
-      if (ok) {
-        orow[n - g.n_begin] = o;
-        if (prow) prow[n - g.n_begin] = p;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int n = n0 + 32 * u + lane;
+        if (ok[u]) {
+          orow[n - g.n_begin] = o[u];
+          if (prow) prow[n - g.n_begin] = p[u];
+        }
       }
     }
     if (a.compression && a.ema_out != nullptr && lane == 0) a.ema_out[(size_t)b * g.F + f] = carry;
