@@ -245,6 +245,13 @@ def main():
             fe(xs[i % N_ROTATE])
         torch.cuda.synchronize()
         n_prof, ms_k0, ms_k1, ms_k2 = LF.profile_end()
+        # effective SM clock of K1: cycles and nanoseconds counted inside the kernel, right after a hot loop
+        k1_cyc = k1_ns = 0
+        if args.algo != "fp32" and LF.tc_supported(F, K, H):
+            for i in range(steps):
+                fe(xs[i % N_ROTATE])
+            prm_t = [None if q is None else q.detach() for q in fe._param_tuple()]
+            k1_cyc, k1_ns = LF.k1_clock_probe(fe.spec, xs[0], *prm_t)
 
     times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -272,6 +279,7 @@ def main():
             "executed_frac": exec_mult * flops_alg / k1_s / 1e12 / peaks["tensor"],
             "executed_note": "3 fp16 products per fp32 product (hi/lo split) and taps padded 401->416",
             "k1_ms": ms_k1, "k0_ms": ms_k0, "k2_ms": ms_k2, "launches_profiled": n_prof,
+            "k1_sm_cycles": k1_cyc, "k1_sm_mhz_effective": (1e3 * k1_cyc / k1_ns) if k1_ns else None,
             "traffic": None,
             "hbm": {"algorithmic_bytes": bytes_alg, "achieved": bytes_alg / k1_s / 1e9, "peak": peaks["hbm"],
                     "unit": "GB/s", "frac": bytes_alg / k1_s / 1e9 / peaks["hbm"],

@@ -117,7 +117,7 @@ int leafk_backward(const leafk_config* cfg, const leafk_params* prm, const float
 size_t leafk_backward_workspace_bytes(const leafk_config* cfg, int B, int T);
 
 /* End-to-end call on HOST buffers: x_host (B,1,T) and out_host (B,F,N) are host pointers
- * (pinned for full speed).  The H2D copy is enqueued on copy_stream in `n_slices` (<= 64) pieces,
+ * (pinned for full speed).  The H2D copy is enqueued on copy_stream in `n_slices` (<= 32) pieces,
  * each followed by a stream-ordered 32-bit flag write; ONE persistent launch of the tensor-core
  * kernel on `stream` consumes clips as their slice lands, so the PCIe transfer and the compute
  * overlap without per-slice launch overheads; PCEN and the D2H copy follow on `stream`.  When
@@ -137,6 +137,12 @@ int leafk_tc_supported(int F, int K, int H);
  * returns the number of forwards seen and the mean milliseconds of each kernel. */
 void leafk_profile_begin(void);
 int leafk_profile_end(float* ms_k0, float* ms_k1, float* ms_k2);
+
+/* While profiling is on (leafk_profile_begin), CTA 0 of the tensor-core kernel stores its SM-cycle count and
+ * its wall time (globaltimer) in the workspace; this reads them back (synchronous copy) for the LAST forward
+ * that used `workspace` with shapes (B,T).  cycles/nanoseconds = effective SM clock in GHz during K1. */
+int leafk_profile_k1_clock(const leafk_config* cfg, int B, int T, const void* workspace, size_t workspace_bytes,
+                           long long* cycles, long long* nanoseconds);
 
 /* Introspection used by tests / bench: kernels launched by this thread since the last reset. */
 long long leafk_launch_count(int reset);

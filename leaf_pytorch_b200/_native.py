@@ -19,7 +19,7 @@ ALGOS = {"auto": ALGO_AUTO, "fp32": ALGO_FP32, "tc": ALGO_TC}
 SYMBOLS = (
     "leafk_version", "leafk_last_error", "leafk_num_frames", "leafk_same_padding",
     "leafk_workspace_bytes", "leafk_forward", "leafk_forward_window", "leafk_backward",
-    "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end",
+    "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end", "leafk_profile_k1_clock",
 )
 
 
@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
         L.leafk_profile_begin.argtypes = []
         L.leafk_profile_end.restype = i
         L.leafk_profile_end.argtypes = [C.POINTER(C.c_float)] * 3
+        L.leafk_profile_k1_clock.restype = i
+        L.leafk_profile_k1_clock.argtypes = [C.POINTER(Config), i, i, vp, sz, C.POINTER(ll), C.POINTER(ll)]
         L.leafk_launch_count.restype = ll
         L.leafk_launch_count.argtypes = [i]
         _lib = L

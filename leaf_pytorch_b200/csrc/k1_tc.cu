@@ -98,6 +98,7 @@ __device__ __forceinline__ void build_copy(tc::Misc* misc, const uint4* sth4, co
 struct TcReady {
   const int* ready;
   int clips_per_flag;
+  long long* perf;      // optional: CTA 0 stores {SM cycles, nanoseconds} of its lifetime (effective SM clock)
 };
 
 struct TcBwdArgs {
@@ -133,6 +134,11 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   Misc* misc = reinterpret_cast<Misc*>(smem + sp.off_misc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long perf_c0 = 0, perf_t0 = 0;
+  if (rdy.perf != nullptr && blockIdx.x == 0 && tid == 0) {
+    perf_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(perf_t0));
+  }
   // CTA pair = cluster of 2 (same TPC).  Both CTAs serve the same channel group; the pair takes two units
   // (tiles) per iteration, rank r the unit 2*pair_unit + r.  Rank 0 issues the MMAs for both.
   const uint32_t rank = cluster_ctarank();
@@ -496,6 +502,12 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   tc_fence_before();
   cluster_sync_all();                        // nobody may still signal a peer barrier / use TMEM
   if (warp == tc::MMA_WARP) tmem_dealloc_pair<512>(tmem);
+  if (rdy.perf != nullptr && blockIdx.x == 0 && tid == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    rdy.perf[0] = clock64() - perf_c0;
+    rdy.perf[1] = t1 - perf_t0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -536,7 +548,7 @@ static cudaError_t launch_bwd_inst_ks(const Geom& g, const float* x, const uint8
   cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 1, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   k1_tc_kernel<CG, NSLOT, 1, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, nullptr, nullptr, n_groups, ba,
-                                                                       TcReady{nullptr, 1});
+                                                                       TcReady{nullptr, 1, nullptr});
   return cudaGetLastError();
 }
 template <int CG, int NSLOT>
@@ -589,8 +601,9 @@ static cudaError_t launch_cg(int nslot, const Geom& g, const float* x, const uin
 }
 
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
-                         int tc_cg, int tc_groups, cudaStream_t stream, const int* ready, int clips_per_flag) {
-  const TcReady rdy{ready, clips_per_flag < 1 ? 1 : clips_per_flag};
+                         int tc_cg, int tc_groups, cudaStream_t stream, const int* ready, int clips_per_flag,
+                         long long* perf) {
+  const TcReady rdy{ready, clips_per_flag < 1 ? 1 : clips_per_flag, perf};
   cudaError_t err;
   const int n_sm = sm_count(&err);
   if (err != cudaSuccess) return err;

@@ -21,7 +21,7 @@ constexpr int F32_TILE = 512;
 bool k1_tc_supported(const Geom& g, const char** why);
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm,
                          float* ppart, int tc_cg, int tc_groups, cudaStream_t stream, const int* ready,
-                         int clips_per_flag);
+                         int clips_per_flag, long long* perf);
 constexpr int TC_TILE = 1024;
 // k2_pcen.cu
 cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cudaStream_t stream);
@@ -115,7 +115,7 @@ static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace
   const int sl32 = (F32_TILE + g.K - 2) / g.H + 1, sltc = (TC_TILE + g.K - 2) / g.H + 1;
   size_t a = (size_t)max_tiles_fp32 * sl32, b = (size_t)max_tiles_tc * sltc;
   off += align256(sizeof(float) * (size_t)g.B * g.F * (a > b ? a : b));
-  w->off_flags = off; off += 256;                      // 64 slice-ready flags (leafk_forward_host)
+  w->off_flags = off; off += 256;                      // 32 slice-ready flags (leafk_forward_host) + 2 perf counters
   w->total = off;
 }
 
@@ -205,7 +205,7 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   if (algo_out) *algo_out = algo;
   if (algo == LEAFK_ALGO_TC)
     err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, stream, clips_per_flag > 0 ? flags : nullptr,
-                       clips_per_flag);
+                       clips_per_flag, g_prof_on ? (long long*)(flags + 32) : nullptr);
   else
     err = launch_k1_fp32(g, x_win, w32, g32, ppart, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k1 launch: %s", cudaGetErrorString(err));
@@ -327,7 +327,7 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
   if (N < 1 || B < 1) return fail(LEAFK_EINVAL, "bad B/T");
   if (n_slices < 1) n_slices = 1;
   if (n_slices > B) n_slices = B;
-  if (n_slices > 64) n_slices = 64;
+  if (n_slices > 32) n_slices = 32;
   int* flags = nullptr;
   int algo = 0;
   int rc = flags_location(cfg, B, T, workspace, workspace_bytes, &flags, &algo);
@@ -341,7 +341,7 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
   // per clip on slice-ready flags that follow each slice of the H2D copy in copy_stream order.
   const int clips_per_flag = (B + n_slices - 1) / n_slices;
   const int n_flags = (B + clips_per_flag - 1) / clips_per_flag;
-  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * 64, stream);
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * 32, stream);
   if (e != cudaSuccess) return fail(LEAFK_ECUDA, "flag reset: %s", cudaGetErrorString(e));
   cudaEvent_t reset_done;
   cudaEventCreateWithFlags(&reset_done, cudaEventDisableTiming);
@@ -408,6 +408,21 @@ int leafk_profile_end(float* ms_k0, float* ms_k1, float* ms_k2) {
     if (ms_k2) *ms_k2 = (float)(acc[2] / n);
   }
   return n;
+}
+
+int leafk_profile_k1_clock(const leafk_config* cfg, int B, int T, const void* workspace, size_t workspace_bytes,
+                           long long* cycles, long long* nanoseconds) {
+  if (!cfg || !workspace || !cycles || !nanoseconds) return fail(LEAFK_EINVAL, "null pointer argument");
+  int* flags = nullptr;
+  int algo = 0;
+  int rc = flags_location(cfg, B, T, const_cast<void*>(workspace), workspace_bytes, &flags, &algo);
+  if (rc) return rc;
+  long long host[2] = {0, 0};
+  cudaError_t e = cudaMemcpy(host, flags + 32, sizeof(host), cudaMemcpyDeviceToHost);   // synchronous: profiling only
+  if (e != cudaSuccess) return fail(LEAFK_ECUDA, "perf read: %s", cudaGetErrorString(e));
+  *cycles = host[0];
+  *nanoseconds = host[1];
+  return LEAFK_OK;
 }
 
 long long leafk_launch_count(int reset) {

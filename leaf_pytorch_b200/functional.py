@@ -253,6 +253,33 @@ def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, a
     return out_host
 
 
+def k1_clock_probe(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w):
+    """Run one forward with profiling on and return (SM cycles, nanoseconds) of the tensor-core kernel's CTA 0:
+    cycles/ns is the SM clock (GHz) the kernel actually ran at."""
+    L = N.lib()
+    x = _check_input(x)
+    B, _, T = x.shape
+    n = spec.num_frames(T)
+    cfg = spec.config()
+    prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, spec.F, n), dtype=torch.float32, device=x.device)
+        ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        L.leafk_profile_begin()
+        rc = L.leafk_forward(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(out), None, _ptr(ws), ws_bytes,
+                             _stream_ptr(x.device))
+        torch.cuda.synchronize(x.device)
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        L.leafk_profile_end(C.byref(a), C.byref(b), C.byref(c))
+        N.check(rc, "leafk_forward")
+        cyc, ns = C.c_longlong(0), C.c_longlong(0)
+        N.check(L.leafk_profile_k1_clock(C.byref(cfg), B, T, _ptr(ws), ws_bytes, C.byref(cyc), C.byref(ns)),
+                "leafk_profile_k1_clock")
+    del keep
+    return int(cyc.value), int(ns.value)
+
+
 def profile_begin() -> None:
     N.lib().leafk_profile_begin()
 

@@ -168,3 +168,27 @@ def test_batch_permutation_equivariance_full_size():
     fe = L.Leaf().cuda()
     with torch.no_grad():
         assert torch.equal(fe(x)[perm], fe(x[perm].contiguous()))
+
+
+def test_forward_is_cuda_graph_capturable():
+    """The 3-launch forward can be captured into a CUDA graph and replayed (no host-side state, no sync,
+    all scratch from the caching allocator)."""
+    case, x, prm, z = load_golden("cfg1_default")
+    fe = build(case, prm, "auto")
+    xg = x.cuda()
+    static_x = xg.clone()
+    with torch.no_grad():
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                fe(static_x)
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = fe(static_x)
+        static_x.copy_(0.5 * xg)
+        graph.replay()
+        torch.cuda.synchronize()
+        want = fe(0.5 * xg)
+    assert torch.equal(static_out, want)
