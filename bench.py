@@ -237,6 +237,16 @@ def main():
             fe.forward_host(xs_host[(2 + i) % N_ROTATE], out_host)     # returns with the result on the host
         barrier()
         e2e_s = time.perf_counter() - t0
+        # same, with 16-bit PCM host buffers converted in the kernel (extra, not the headline)
+        pcm_host = [(xh * 32767.0).round().to(torch.int16).pin_memory() for xh in xs_host[:4]]
+        for i in range(2):
+            fe.forward_host(pcm_host[i % 4], out_host)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            fe.forward_host(pcm_host[(2 + i) % 4], out_host)
+        barrier()
+        pcm_s = time.perf_counter() - t0
         clocks = sampler.stop() if rank == 0 else None
 
         # --------------------------------------------------------- per-kernel durations (roofline)
@@ -253,10 +263,10 @@ def main():
             prm_t = [None if q is None else q.detach() for q in fe._param_tuple()]
             k1_cyc, k1_ns = LF.k1_clock_probe(fe.spec, xs[0], *prm_t)
 
-    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms_total, e2e_s * 1e3, pcm_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(times[0]), float(times[1])
+    ms_total, e2e_ms, pcm_ms = float(times[0]), float(times[1]), float(times[2])
 
     if rank == 0:
         audio_s_step = world * B * T / SR
@@ -305,6 +315,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * T * 4,
                     "d2h_bytes_per_step": world * B * F * n_frames * 4, "ms_per_step": e2e_ms / steps,
                     "api": "Leaf.forward_host -> leafk_forward_host (pinned host in/out; H2D in 8 slices with ready flags, one persistent launch)"},
+            "e2e_pcm16": {"value": audio_s_step * steps / (pcm_ms * 1e-3), "unit": UNIT,
+                          "h2d_bytes_per_step": world * B * T * 2, "d2h_bytes_per_step": world * B * F * n_frames * 4,
+                          "ms_per_step": pcm_ms / steps,
+                          "note": "same call with int16 PCM host buffers (LEAFK_INPUT_S16, s/32768 in the kernel)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
         }

@@ -31,6 +31,11 @@ extern "C" {
 #define LEAFK_ECUDA (-3)      /* a CUDA runtime call or kernel launch failed                 */
 #define LEAFK_EWINDOW (-4)    /* streaming window does not cover the samples the frames need */
 
+/* Waveform sample type.  With LEAFK_INPUT_S16 every `const float* x` argument points to int16_t samples
+ * (same shapes and strides, in elements). */
+#define LEAFK_INPUT_F32 0
+#define LEAFK_INPUT_S16 1
+
 /* Which conv kernel computes the Gabor filterbank stage. */
 #define LEAFK_ALGO_AUTO 0
 #define LEAFK_ALGO_FP32 1     /* direct FP32-FMA correlation (CUDA cores)                    */
@@ -72,6 +77,9 @@ typedef struct leafk_config {
   float clamp_min; /* 1e-5                                      frontend.py:84      */
   int compression; /* 1: PCEN (frontend.py:65-73)  0: none (frontend.py:74-75)      */
   int algo;        /* LEAFK_ALGO_*                                                  */
+  int input_format;/* LEAFK_INPUT_F32 (reference layout) or LEAFK_INPUT_S16: 16-bit PCM, converted
+                      in the kernel as s/32768 (what soundfile hands the reference's data pipeline,
+                      utilities/data/utils.py:136-157); halves the HBM / PCIe bytes of the waveform */
 } leafk_config;
 
 int leafk_version(void);

@@ -37,7 +37,7 @@ class Grads(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("F", C.c_int), ("K", C.c_int), ("H", C.c_int), ("pcen_floor", C.c_float),
-                ("clamp_min", C.c_float), ("compression", C.c_int), ("algo", C.c_int)]
+                ("clamp_min", C.c_float), ("compression", C.c_int), ("algo", C.c_int), ("input_format", C.c_int)]
 
 
 _lib = None

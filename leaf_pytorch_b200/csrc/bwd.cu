@@ -321,6 +321,7 @@ int bwd_run(const leafk_config* cfg, const leafk_params* prm, const float* x, in
   g.T_total = T; g.t_off = 0; g.T_win = T; g.ldx = T;
   g.N_total = pl.N; g.n_begin = 0; g.n_count = pl.N;
   g.te_lo = 0; g.te_hi = T; g.TL = tc::TILE; g.n_tiles = pl.n_tiles; g.SL = pl.SL;
+  g.x_fmt = cfg->input_format == LEAFK_INPUT_S16 ? 1 : 0;
 
   PcenBwdArgs pa;
   pa.p = saved_p; pa.gout = grad_out; pa.alpha = prm->alpha; pa.delta = prm->delta; pa.root = prm->root;

@@ -186,7 +186,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       const bool valid = u < n_units;                // odd unit count: the last pair's rank 1 runs on zeros
       const int b = valid ? (int)(u / g.n_tiles) : 0, tile = valid ? (int)(u % g.n_tiles) : 0;
       const long long ts = g.te_lo + (long long)tile * TILE;
-      const float* xrow = x + (size_t)b * g.ldx;
+      const size_t xrow = (size_t)b * g.ldx;
       if (valid && rdy.ready != nullptr && ptid == 0) {       // clip b still in flight over PCIe?
         const int* flag = rdy.ready + b / rdy.clips_per_flag;
         int v;
@@ -201,7 +201,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       for (int i = ptid; i < sp.LX; i += PROD_THREADS) {
         const long long a = ts - g.padL + i, wi = a - g.t_off;
         float v = 0.f;
-        if (valid && a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win) v = xrow[wi];   // coherent load: may have just landed
+        if (valid && a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win) v = load_sample(x, xrow, wi, g.x_fmt);   // coherent load: may have just landed
         s_st32[i] = v;
         mx = fmaxf(mx, fabsf(v));
       }

@@ -70,6 +70,8 @@ static int make_geom(const leafk_config* cfg, int B, long long ldx, long long T_
                      int T_win, int n_begin, int n_count, int tile_len, Geom* out) {
   if (!cfg) return fail(LEAFK_EINVAL, "null config");
   if (cfg->F < 1 || cfg->K < 2 || cfg->H < 1) return fail(LEAFK_EINVAL, "bad F/K/H (%d,%d,%d)", cfg->F, cfg->K, cfg->H);
+  if (cfg->input_format != LEAFK_INPUT_F32 && cfg->input_format != LEAFK_INPUT_S16)
+    return fail(LEAFK_EINVAL, "unknown input_format %d", cfg->input_format);
   if (B < 1 || T_total < 1 || T_win < 1) return fail(LEAFK_EINVAL, "bad B/T (%d,%lld,%d)", B, T_total, T_win);
   if (T_total > (1LL << 30)) return fail(LEAFK_EINVAL, "clip too long (%lld samples)", T_total);
   Geom g;
@@ -89,6 +91,7 @@ static int make_geom(const leafk_config* cfg, int B, long long ldx, long long T_
   long long hi = (long long)(n_begin + n_count - 1) * g.H - g.padL + g.K;   // exclusive
   g.te_lo = lo < 0 ? 0 : lo;
   g.te_hi = hi > T_total ? T_total : hi;
+  g.x_fmt = cfg->input_format == LEAFK_INPUT_S16 ? 1 : 0;
   g.TL = tile_len;
   g.n_tiles = (int)((g.te_hi - g.te_lo + tile_len - 1) / tile_len);
   g.SL = (tile_len + g.K - 2) / g.H + 1;
@@ -292,12 +295,14 @@ static int forward_host_sliced(const leafk_config* cfg, const leafk_params* prm,
     if (nb == 0) continue;
     cudaEventCreateWithFlags(&up[made], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&done[made], cudaEventDisableTiming);
-    cudaError_t e = cudaMemcpyAsync(dev_x + (size_t)b0 * T, x_host + (size_t)b0 * T, sizeof(float) * (size_t)nb * T,
+    const size_t esz = cfg->input_format == LEAFK_INPUT_S16 ? 2 : 4;
+    const size_t xoff = (size_t)b0 * T * esz;
+    cudaError_t e = cudaMemcpyAsync((uint8_t*)dev_x + xoff, (const uint8_t*)x_host + xoff, esz * (size_t)nb * T,
                                     cudaMemcpyHostToDevice, cstream);
     if (e != cudaSuccess) { rc = fail(LEAFK_ECUDA, "H2D: %s", cudaGetErrorString(e)); ++made; break; }
     if (two) { cudaEventRecord(up[made], cstream); cudaStreamWaitEvent(stream, up[made], 0); }
-    rc = leafk_forward(cfg, prm, dev_x + (size_t)b0 * T, nb, T, dev_out + (size_t)b0 * cfg->F * N, nullptr,
-                       workspace, workspace_bytes, stream);
+    rc = leafk_forward(cfg, prm, (const float*)((const uint8_t*)dev_x + xoff), nb, T, dev_out + (size_t)b0 * cfg->F * N,
+                       nullptr, workspace, workspace_bytes, stream);
     if (rc == LEAFK_OK) {
       if (two) { cudaEventRecord(done[made], stream); cudaStreamWaitEvent(cstream, done[made], 0); }
       e = cudaMemcpyAsync(out_host + (size_t)b0 * cfg->F * N, dev_out + (size_t)b0 * cfg->F * N,
@@ -350,8 +355,9 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
   cudaEventDestroy(reset_done);
   for (int s = 0; s < n_flags; ++s) {
     const int b0 = s * clips_per_flag, b1 = (b0 + clips_per_flag < B) ? b0 + clips_per_flag : B;
-    e = cudaMemcpyAsync(dev_x + (size_t)b0 * T, x_host + (size_t)b0 * T, sizeof(float) * (size_t)(b1 - b0) * T,
-                        cudaMemcpyHostToDevice, cstream);
+    const size_t esz = cfg->input_format == LEAFK_INPUT_S16 ? 2 : 4;
+    e = cudaMemcpyAsync((uint8_t*)dev_x + (size_t)b0 * T * esz, (const uint8_t*)x_host + (size_t)b0 * T * esz,
+                        esz * (size_t)(b1 - b0) * T, cudaMemcpyHostToDevice, cstream);
     if (e != cudaSuccess) return fail(LEAFK_ECUDA, "H2D: %s", cudaGetErrorString(e));
     if (write32(cstream, (unsigned long long)(uintptr_t)(flags + s), 1u, 0u) != 0)
       return fail(LEAFK_ECUDA, "cuStreamWriteValue32 failed");

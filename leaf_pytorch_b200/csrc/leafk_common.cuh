@@ -31,7 +31,14 @@ struct Geom {
   int TL;                  // tile length in e-samples
   int n_tiles;             // tiles per clip
   int SL;                  // slots (frames) a tile can touch
+  int x_fmt;               // 0: float32 samples, 1: int16 PCM (value = s / 32768)
 };
+
+// sample i of a clip row (row = first sample of the clip in the window buffer)
+__device__ __forceinline__ float load_sample(const float* base, size_t row_elems, long long i, int fmt) {
+  if (fmt == 0) return base[row_elems + i];
+  return (float)reinterpret_cast<const short*>(base)[row_elems + i] * (1.0f / 32768.0f);
+}
 
 __host__ __device__ inline long long floordiv_ll(long long a, long long b) {
   return (a >= 0) ? a / b : -((-a + b - 1) / b);

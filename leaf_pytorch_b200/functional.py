@@ -29,9 +29,9 @@ class LeafSpec:
     pcen_floor: float = PCEN_FLOOR
     clamp_min: float = CLAMP_MIN
 
-    def config(self) -> N.Config:
+    def config(self, input_dtype=torch.float32) -> N.Config:
         return N.Config(self.F, self.K, self.H, self.pcen_floor, self.clamp_min, int(self.compression),
-                        N.ALGOS[self.algo])
+                        N.ALGOS[self.algo], 1 if input_dtype == torch.int16 else 0)
 
     def num_frames(self, T: int) -> int:
         lo = self.K // 2 + self.K % 2 - 1
@@ -66,8 +66,8 @@ def _check_input(x: torch.Tensor) -> torch.Tensor:
         raise N.LeafNativeError(
             "leaf_pytorch_b200 runs only on CUDA tensors (sm_100a kernels); there is no CPU fallback. "
             "Move the module and the input to a GPU.")
-    if x.dtype != torch.float32:
-        raise TypeError(f"input must be float32, got {x.dtype}")
+    if x.dtype not in (torch.float32, torch.int16):
+        raise TypeError(f"input must be float32 (or int16 PCM, read as s/32768), got {x.dtype}")
     if x.dim() != 3 or x.shape[1] != 1:
         raise ValueError(f"input must have shape (B,1,T), got {tuple(x.shape)}")
     if x.shape[0] < 1 or x.shape[2] < 1:
@@ -93,7 +93,7 @@ def forward_raw(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, e
     x = _check_input(x)
     B, _, T = x.shape
     n = spec.num_frames(T)
-    cfg = spec.config()
+    cfg = spec.config(x.dtype)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
     with torch.cuda.device(x.device):
         out = torch.empty((B, spec.F, n), dtype=torch.float32, device=x.device)
@@ -115,7 +115,7 @@ def forward_window(spec: LeafSpec, x_win, T_total: int, t_off: int, n_begin: int
     L = N.lib()
     x_win = _check_input(x_win)
     B, _, T_win = x_win.shape
-    cfg = spec.config()
+    cfg = spec.config(x_win.dtype)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x_win.device)
     with torch.cuda.device(x_win.device):
         if out is None:
@@ -173,7 +173,7 @@ class _LeafFunction(torch.autograd.Function):
             alpha, delta, root, ema_w = saved[idx:idx + 4]
         x = _check_input(x)
         B, _, T = x.shape
-        cfg = spec.config()
+        cfg = spec.config(x.dtype)
         prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
         grad_out = grad_out.contiguous().to(torch.float32)
         dev = x.device
@@ -182,7 +182,7 @@ class _LeafFunction(torch.autograd.Function):
                 return None if t is None else torch.zeros(t.numel(), dtype=torch.float32, device=dev)
             g = [z(kernel), z(pool_w), z(pool_b), z(alpha), z(delta), z(root), z(ema_w)]
             grads = N.Grads(*[None if t is None else t.data_ptr() for t in g])
-            gx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+            gx = torch.empty(x.shape, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
             ws_bytes = L.leafk_backward_workspace_bytes(C.byref(cfg), B, T)
             ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
             rc = L.leafk_backward(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(grad_out), _ptr(p),
@@ -216,15 +216,15 @@ def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, a
     (B,1,T) float32 CPU (pinned for full speed); returns ``out_host`` (B,F,N) pinned CPU.  The call
     synchronises the compute stream before returning (the result is on the host)."""
     L = N.lib()
-    if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 3 or x_host.shape[1] != 1:
-        raise ValueError("x_host must be a float32 CPU tensor of shape (B,1,T)")
+    if x_host.is_cuda or x_host.dtype not in (torch.float32, torch.int16) or x_host.dim() != 3 or x_host.shape[1] != 1:
+        raise ValueError("x_host must be a float32 (or int16 PCM) CPU tensor of shape (B,1,T)")
     device = torch.device(device if device is not None else kernel.device)
     if device.type != "cuda":
         raise N.LeafNativeError("forward_host needs the parameters on a CUDA device; there is no CPU fallback")
     x_host = x_host.contiguous()
     B, _, T = x_host.shape
     n = spec.num_frames(T)
-    cfg = spec.config()
+    cfg = spec.config(x_host.dtype)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, device)
     if out_host is None:
         out_host = torch.empty((B, spec.F, n), dtype=torch.float32, pin_memory=True)
@@ -232,12 +232,12 @@ def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, a
             or not out_host.is_contiguous():
         raise ValueError("out_host must be a contiguous float32 CPU tensor of shape (B,F,N)")
     with torch.cuda.device(device):
-        key = (device.index, B, T, spec.F, n)
+        key = (device.index, B, T, spec.F, n, x_host.dtype)
         bufs = _host_cache.get(key)
         if bufs is None:
             _host_cache.clear()
             ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n)
-            bufs = (torch.empty(B * T, dtype=torch.float32, device=device),
+            bufs = (torch.empty(B * T, dtype=x_host.dtype, device=device),
                     torch.empty(B * spec.F * n, dtype=torch.float32, device=device),
                     torch.empty(ws_bytes, dtype=torch.uint8, device=device), torch.cuda.Stream(device=device))
             _host_cache[key] = bufs
@@ -260,7 +260,7 @@ def k1_clock_probe(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root
     x = _check_input(x)
     B, _, T = x.shape
     n = spec.num_frames(T)
-    cfg = spec.config()
+    cfg = spec.config(x.dtype)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
     with torch.cuda.device(x.device):
         out = torch.empty((B, spec.F, n), dtype=torch.float32, device=x.device)

@@ -192,3 +192,30 @@ def test_forward_is_cuda_graph_capturable():
         torch.cuda.synchronize()
         want = fe(0.5 * xg)
     assert torch.equal(static_out, want)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_int16_pcm_input_equals_float_path(algo):
+    """LEAFK_INPUT_S16: 16-bit PCM converted in the kernel as s/32768 (exact in fp32), so the result must be
+    bit-identical to feeding the converted float waveform -- forward, host-pipelined forward and gradients."""
+    case, x, prm, z = load_golden("pcm16_default")
+    fe = build(case, prm, algo)
+    pcm = torch.round(x * 32768.0).clamp_(-32768, 32767).to(torch.int16)
+    xf = pcm.to(torch.float32) / 32768.0
+    assert torch.equal(xf, x)                                  # the golden input is already PCM-quantised
+    with torch.no_grad():
+        a = fe(pcm.cuda())
+        b = fe(xf.cuda())
+    assert torch.equal(a, b)
+    assert_close(a.cpu().numpy(), z["out"], f"pcm16/{algo}")
+    got = fe.forward_host(pcm.pin_memory(), n_slices=2)
+    assert torch.equal(got, a.cpu())
+    if algo == "tc":
+        G = torch.randn(a.shape, generator=torch.Generator().manual_seed(3)).cuda()
+        grads = []
+        for inp in (pcm.cuda(), xf.cuda()):
+            fe.zero_grad(set_to_none=True)
+            (fe(inp) * G).sum().backward()
+            grads.append([p.grad.clone() for p in fe.parameters()])
+        for ga, gb in zip(*grads):
+            assert torch.equal(ga, gb)
