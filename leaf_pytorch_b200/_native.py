@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libl
 
 ALGO_AUTO, ALGO_FP32, ALGO_TC = 0, 1, 2
 ALGOS = {"auto": ALGO_AUTO, "fp32": ALGO_FP32, "tc": ALGO_TC}
+BWD_2PRODUCT = 16
 
 SYMBOLS = (
     "leafk_version", "leafk_last_error", "leafk_num_frames", "leafk_same_padding",

@@ -26,7 +26,7 @@ void launch_k0_bwd(const float* kernel, const float* pool_w, int F, int K, int K
 void bank_bounds(int K, float* mu_hi, float* sigma_lo, float* sigma_hi, float* pool_lo);
 cudaError_t launch_k1_tc_bwd(const Geom& g, const float* x, const uint8_t* w16b, int FB, int n_groups,
                              const float* dpT, const float* bprm, float* bpart, int* ctas_per_group,
-                             cudaStream_t stream);
+                             int skip_xlo, cudaStream_t stream);
 
 constexpr int B1_FPB = 8;      // filters per block (= warps)
 constexpr int B1_SEG = 128;    // frames per scan step
@@ -340,7 +340,8 @@ int bwd_run(const leafk_config* cfg, const leafk_params* prm, const float* x, in
   err = cudaMemsetAsync(bpart, 0, sizeof(float) * (size_t)pl.max_ctas * pl.Fpad * 4, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "bpart reset: %s", cudaGetErrorString(err));
   int ctas_per_group = 0;
-  err = launch_k1_tc_bwd(g, x, w16b, pl.FB, pl.n_groups, dpT, bprm, bpart, &ctas_per_group, stream);
+  const int skip_xlo = (cfg->algo & LEAFK_BWD_2PRODUCT) ? 1 : 0;
+  err = launch_k1_tc_bwd(g, x, w16b, pl.FB, pl.n_groups, dpT, bprm, bpart, &ctas_per_group, skip_xlo, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k1_tc_bwd launch: %s", cudaGetErrorString(err));
   if (ctas_per_group > pl.max_ctas) return fail(LEAFK_EINVAL, "internal: partial buffer too small");
 

@@ -106,6 +106,8 @@ struct TcBwdArgs {
   const float* bprm;    // (Fpad, 8): [0] pooling exp2 coefficient, [1..3] power-of-two shifts of the y,z,v banks
   float* bpart;         // (ctas_per_group, Fpad, 4) per-CTA partial sums: {S_mu, S_sigma, S_poolw, 0}
   int Fpad;             // n_groups * FB
+  int skip_xlo;         // 1: drop the x_lo*W_hi product (2-product mode): the waveform enters with fp16 rounding
+                        //    (zero-mean, averages out over the B*T terms of a gradient), the banks keep hi+lo
 };
 
 // KS > 0: number of k-steps known at compile time (26 for the default 401-tap window): the MMA issue loop is
@@ -258,7 +260,11 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
           const uint64_t a_hi = smem_desc(a_base + (uint32_t)((2 * p) * sp.acb), 16, 128);
           const uint64_t a_lo = smem_desc(a_base + (uint32_t)((2 * p + 1) * sp.acb), 16, 128);
           if (leader) {
-            if constexpr (KS > 0) {
+            if (MODE == 1 && ba.skip_xlo) {
+#pragma unroll 4
+              for (int ks = 0; ks < ksteps; ++ks)
+                mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)ks * b1_step, IDESC_MAIN, ks > 0);
+            } else if constexpr (KS > 0) {
 #pragma unroll
               for (int ks = 0; ks < KS; ++ks) {
                 mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)(ks * ((CG * 32) >> 4)), IDESC_MAIN, ks > 0);
@@ -528,7 +534,7 @@ static cudaError_t launch_inst_ks(const Geom& g, const float* x, const uint8_t* 
                                   int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy) {
   cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
-  TcBwdArgs none{nullptr, nullptr, nullptr, 0};
+  TcBwdArgs none{nullptr, nullptr, nullptr, 0, 0};
   k1_tc_kernel<CG, NSLOT, 0, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups, none, rdy);
   return cudaGetLastError();
 }
@@ -578,13 +584,13 @@ static int sm_count(cudaError_t* err) {
 // group through *ctas_per_group (rows of bpart the final reduction must add).
 cudaError_t launch_k1_tc_bwd(const Geom& g, const float* x, const uint8_t* w16b, int FB, int n_groups,
                              const float* dpT, const float* bprm, float* bpart, int* ctas_per_group,
-                             cudaStream_t stream) {
+                             int skip_xlo, cudaStream_t stream) {
   cudaError_t err;
   const int n_sm = sm_count(&err);
   if (err != cudaSuccess) return err;
   const int grid = tc::pair_grid(n_sm, n_groups, (long long)g.B * g.n_tiles);
   *ctas_per_group = 2 * (((grid / 2) + n_groups - 1) / n_groups);   // rows of bpart (zero-filled by the caller)
-  TcBwdArgs ba{dpT, bprm, bpart, n_groups * FB};
+  TcBwdArgs ba{dpT, bprm, bpart, n_groups * FB, skip_xlo};
   const int nslot = tc::slots_per_thread(g.K, g.H);
   if (FB == 16 && nslot <= 3) return launch_bwd_inst<96, 3>(g, x, w16b, n_groups, grid, ba, stream);
   if (FB == 8 && nslot <= 3) return launch_bwd_inst<48, 3>(g, x, w16b, n_groups, grid, ba, stream);

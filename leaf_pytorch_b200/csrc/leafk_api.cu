@@ -58,10 +58,11 @@ int fail(int code, const char* fmt, ...) {
 void count_launch(int n) { g_launches += n; }
 
 static int pick_algo(const leafk_config* cfg, const Geom& g) {
-  if (cfg->algo == LEAFK_ALGO_FP32) return LEAFK_ALGO_FP32;
+  const int want = cfg->algo & 15;                       // low bits: kernel choice; high bits: flags
+  if (want == LEAFK_ALGO_FP32) return LEAFK_ALGO_FP32;
   const char* why = nullptr;
   const bool ok = k1_tc_supported(g, &why);
-  if (cfg->algo == LEAFK_ALGO_TC) return ok ? LEAFK_ALGO_TC : -1;
+  if (want == LEAFK_ALGO_TC) return ok ? LEAFK_ALGO_TC : -1;
   return ok ? LEAFK_ALGO_TC : LEAFK_ALGO_FP32;
 }
 

@@ -28,10 +28,12 @@ class LeafSpec:
     algo: str = "auto"
     pcen_floor: float = PCEN_FLOOR
     clamp_min: float = CLAMP_MIN
+    fast_backward: bool = False      # LEAFK_BWD_2PRODUCT: drop the x_lo*W_hi product in the backward correlations
 
     def config(self, input_dtype=torch.float32) -> N.Config:
+        algo = N.ALGOS[self.algo] | (N.BWD_2PRODUCT if self.fast_backward else 0)
         return N.Config(self.F, self.K, self.H, self.pcen_floor, self.clamp_min, int(self.compression),
-                        N.ALGOS[self.algo], 1 if input_dtype == torch.int16 else 0)
+                        algo, 1 if input_dtype == torch.int16 else 0)
 
     def num_frames(self, T: int) -> int:
         lo = self.K // 2 + self.K % 2 - 1
@@ -178,8 +180,8 @@ class _LeafFunction(torch.autograd.Function):
         grad_out = grad_out.contiguous().to(torch.float32)
         dev = x.device
         with torch.cuda.device(dev):
-            def z(t):
-                return None if t is None else torch.zeros(t.numel(), dtype=torch.float32, device=dev)
+            def z(t):                                    # leafk_backward writes (does not accumulate) every entry
+                return None if t is None else torch.empty(t.numel(), dtype=torch.float32, device=dev)
             g = [z(kernel), z(pool_w), z(pool_b), z(alpha), z(delta), z(root), z(ema_w)]
             grads = N.Grads(*[None if t is None else t.data_ptr() for t in g])
             gx = torch.empty(x.shape, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
