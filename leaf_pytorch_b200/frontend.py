@@ -191,6 +191,9 @@ class Leaf(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """reference frontend.py:78-89, fused."""
+        if isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 3 and x.shape[0] == 0 and x.shape[2] > 0:
+            # empty batch: the reference returns an empty (0,F,N) tensor (conv1d accepts B = 0)
+            return torch.zeros((0, self.spec.F, self.spec.num_frames(x.shape[2])), dtype=torch.float32, device=x.device)
         return LF.leaf_forward(self.spec, x, *self._param_tuple())
 
     def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,

