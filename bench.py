@@ -279,7 +279,7 @@ def main():
         algo_used = "tc" if (args.algo != "fp32" and LF.tc_supported(F, K, H)) else "fp32"
         exec_mult = 3.0 * ((K + 15) // 16 * 16) / K if algo_used == "tc" else 1.0
         roofline = {
-            "kernel": "k1_tc_kernel<80,3> (Gabor Toeplitz GEMM + modulus + pooling partials)" if algo_used == "tc"
+            "kernel": "k1_tc_kernel<80,3,0,26> on CTA pairs (Gabor Toeplitz GEMM + modulus + pooling partials)" if algo_used == "tc"
             else "k1_fp32_kernel",
             "bound": "tensor" if algo_used == "tc" else "fp32-fma",
             "achieved": flops_alg / k1_s / 1e12, "peak": peaks["tensor"], "unit": "TFLOP/s",
