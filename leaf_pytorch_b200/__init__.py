@@ -5,6 +5,7 @@ from .frontend import Leaf
 from .frontend_helper import get_frontend
 from .functional import LeafSpec, leaf_forward, forward_raw, forward_window, launch_count
 from ._native import LeafNativeError, LIB_PATH
+from . import integration, streaming, distributed
 
 __all__ = ["Leaf", "get_frontend", "LeafSpec", "leaf_forward", "forward_raw", "forward_window",
            "launch_count", "LeafNativeError", "LIB_PATH"]

@@ -196,3 +196,39 @@ def test_plain_c_client_compiles_links_and_runs_host_calls(tmp_path):
                     "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert "libleafk version 100, 100 frames per clip" in out
+
+
+@pytest.mark.reference
+def test_install_patches_and_restores_the_reference():
+    from leaf_pytorch_b200 import integration
+    sys.path.insert(0, "/root/reference")
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            import models.classifier as MC
+            import leaf_pytorch.frontend as RF
+            ref_leaf, ref_factory = RF.Leaf, MC.get_frontend
+            done = integration.install()
+            assert done["models.classifier.get_frontend"] and done["leaf_pytorch.frontend.Leaf"]
+            cfg = {"frontend": {"name": "leaf", "default_args": True}, "audio_config": {"sample_rate": 16000},
+                   "model": {"arch": "resnet", "num_classes": 35, "model_depth": 18, "pool": "avgpool", "type": "multiclass"}}
+            clf = MC.Classifier(cfg)
+            assert isinstance(clf.features, L.Leaf) and RF.Leaf is L.Leaf
+            integration.uninstall()
+            assert RF.Leaf is ref_leaf and MC.get_frontend is ref_factory
+    finally:
+        sys.path.remove("/root/reference")
+        for m in [m for m in sys.modules if m.split(".")[0] in ("leaf_pytorch", "models")]:
+            del sys.modules[m]
+
+
+def test_bench_reference_arm_prints_contract_json():
+    """bench.py --impl reference runs on CPU (the oracle port) and prints one JSON line with the contract keys."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], check=True, capture_output=True, text=True, timeout=600).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "audio_seconds_per_second" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+    assert "workload" in line["config"] and line["vs_baseline"] is None
