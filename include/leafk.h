@@ -143,6 +143,21 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
                        int T, float* out_host, int n_slices, float* dev_x, float* dev_out,
                        void* workspace, size_t workspace_bytes, void* stream, void* copy_stream);
 
+/* Fully asynchronous variant for serving loops that keep several batches in flight.  One call = one buffer SET
+ * (dev_x, dev_out, workspace, the two events) -- use as many sets as batches in flight.  Ordering enforced
+ * inside: H2D slices + ready flags on copy_stream (after the set's previous compute finished), the persistent
+ * forward on `stream`, the D2H on d2h_stream (three distinct streams).  ev_compute_done / ev_out_ready are
+ * (re)recorded by the call; out_host is valid once ev_out_ready has completed (leafk_event_synchronize).
+ * Successive calls overlap: the H2D of batch i+1 runs under the kernels of batch i, the D2H of batch i under
+ * the kernels of batch i+1.  Tensor-core kernel only. */
+int leafk_forward_host_async(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B,
+                             int T, float* out_host, int n_slices, float* dev_x, float* dev_out,
+                             void* workspace, size_t workspace_bytes, void* stream, void* copy_stream,
+                             void* d2h_stream, void* ev_compute_done, void* ev_out_ready);
+void* leafk_event_create(void);            /* cudaEvent_t without timing, or NULL */
+void leafk_event_destroy(void* ev);
+int leafk_event_synchronize(void* ev);
+
 /* 1 when LEAFK_ALGO_TC covers (F,K,H); LEAFK_ALGO_AUTO falls back to LEAFK_ALGO_FP32 otherwise. */
 int leafk_tc_supported(int F, int K, int H);
 

@@ -21,6 +21,7 @@ SYMBOLS = (
     "leafk_version", "leafk_last_error", "leafk_num_frames", "leafk_same_padding",
     "leafk_workspace_bytes", "leafk_forward", "leafk_forward_window", "leafk_backward",
     "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end", "leafk_profile_k1_clock",
+    "leafk_forward_host_async", "leafk_event_create", "leafk_event_destroy", "leafk_event_synchronize",
 )
 
 
@@ -88,6 +89,15 @@ def lib() -> C.CDLL:
         L.leafk_profile_end.argtypes = [C.POINTER(C.c_float)] * 3
         L.leafk_profile_k1_clock.restype = i
         L.leafk_profile_k1_clock.argtypes = [C.POINTER(Config), i, i, vp, sz, C.POINTER(ll), C.POINTER(ll)]
+        L.leafk_forward_host_async.restype = i
+        L.leafk_forward_host_async.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, i, vp, vp, vp, sz,
+                                               vp, vp, vp, vp, vp]
+        L.leafk_event_create.restype = vp
+        L.leafk_event_create.argtypes = []
+        L.leafk_event_destroy.restype = None
+        L.leafk_event_destroy.argtypes = [vp]
+        L.leafk_event_synchronize.restype = i
+        L.leafk_event_synchronize.argtypes = [vp]
         L.leafk_launch_count.restype = ll
         L.leafk_launch_count.argtypes = [i]
         _lib = L

@@ -371,6 +371,73 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
   return LEAFK_OK;
 }
 
+void* leafk_event_create(void) {
+  cudaEvent_t ev = nullptr;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  return (void*)ev;
+}
+void leafk_event_destroy(void* ev) { if (ev) cudaEventDestroy((cudaEvent_t)ev); }
+int leafk_event_synchronize(void* ev) {
+  if (!ev) return fail(LEAFK_EINVAL, "null event");
+  cudaError_t e = cudaEventSynchronize((cudaEvent_t)ev);
+  return e == cudaSuccess ? LEAFK_OK : fail(LEAFK_ECUDA, "event sync: %s", cudaGetErrorString(e));
+}
+
+int leafk_forward_host_async(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B, int T,
+                             float* out_host, int n_slices, float* dev_x, float* dev_out, void* workspace,
+                             size_t workspace_bytes, void* stream_, void* copy_stream_, void* d2h_stream_,
+                             void* ev_compute_done_, void* ev_out_ready_) {
+  if (!cfg || !prm || !x_host || !out_host || !dev_x || !dev_out || !workspace || !ev_compute_done_ || !ev_out_ready_)
+    return fail(LEAFK_EINVAL, "null pointer argument");
+  cudaStream_t stream = (cudaStream_t)stream_, cstream = (cudaStream_t)copy_stream_, dstream = (cudaStream_t)d2h_stream_;
+  cudaEvent_t ev_compute_done = (cudaEvent_t)ev_compute_done_, ev_out_ready = (cudaEvent_t)ev_out_ready_;
+  if (cstream == stream || dstream == stream || cstream == dstream)
+    return fail(LEAFK_EINVAL, "leafk_forward_host_async needs three distinct streams");
+  const int N = leafk_num_frames(T, cfg->K, cfg->H);
+  if (N < 1 || B < 1) return fail(LEAFK_EINVAL, "bad B/T");
+  if (n_slices < 1) n_slices = 1;
+  if (n_slices > B) n_slices = B;
+  if (n_slices > 32) n_slices = 32;
+  int* flags = nullptr;
+  int algo = 0;
+  int rc = flags_location(cfg, B, T, workspace, workspace_bytes, &flags, &algo);
+  if (rc) return rc;
+  StreamWriteValue32Fn write32 = stream_write_value32();
+  if (algo != LEAFK_ALGO_TC || write32 == nullptr)
+    return fail(LEAFK_EINVAL, "leafk_forward_host_async needs the tensor-core kernel and cuStreamWriteValue32");
+  const size_t esz = cfg->input_format == LEAFK_INPUT_S16 ? 2 : 4;
+  // copy stream: the previous use of this buffer set (dev_x, flags) must have been consumed
+  cudaStreamWaitEvent(cstream, ev_compute_done, 0);             // no-op for a never-recorded event
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(int) * 32, cstream);
+  if (e != cudaSuccess) return fail(LEAFK_ECUDA, "flag reset: %s", cudaGetErrorString(e));
+  cudaEvent_t reset_done;
+  cudaEventCreateWithFlags(&reset_done, cudaEventDisableTiming);
+  cudaEventRecord(reset_done, cstream);
+  cudaStreamWaitEvent(stream, reset_done, 0);                  // K1 must not poll flags of the previous use
+  cudaEventDestroy(reset_done);
+  const int clips_per_flag = (B + n_slices - 1) / n_slices;
+  const int n_flags = (B + clips_per_flag - 1) / clips_per_flag;
+  for (int s = 0; s < n_flags; ++s) {
+    const int b0 = s * clips_per_flag, b1 = (b0 + clips_per_flag < B) ? b0 + clips_per_flag : B;
+    e = cudaMemcpyAsync((uint8_t*)dev_x + (size_t)b0 * T * esz, (const uint8_t*)x_host + (size_t)b0 * T * esz,
+                        esz * (size_t)(b1 - b0) * T, cudaMemcpyHostToDevice, cstream);
+    if (e != cudaSuccess) return fail(LEAFK_ECUDA, "H2D: %s", cudaGetErrorString(e));
+    if (write32(cstream, (unsigned long long)(uintptr_t)(flags + s), 1u, 0u) != 0)
+      return fail(LEAFK_ECUDA, "cuStreamWriteValue32 failed");
+  }
+  // compute stream: the previous D2H out of dev_out must be over before K2 overwrites it
+  cudaStreamWaitEvent(stream, ev_out_ready, 0);
+  rc = forward_impl(cfg, prm, dev_x, B, T, T, 0, T, 0, N, nullptr, nullptr, dev_out, nullptr, (long long)cfg->F * N, N,
+                    workspace, workspace_bytes, stream, clips_per_flag, nullptr, nullptr);
+  if (rc) return rc;
+  cudaEventRecord(ev_compute_done, stream);
+  cudaStreamWaitEvent(dstream, ev_compute_done, 0);
+  e = cudaMemcpyAsync(out_host, dev_out, sizeof(float) * (size_t)B * cfg->F * N, cudaMemcpyDeviceToHost, dstream);
+  if (e != cudaSuccess) return fail(LEAFK_ECUDA, "D2H: %s", cudaGetErrorString(e));
+  cudaEventRecord(ev_out_ready, dstream);
+  return LEAFK_OK;
+}
+
 size_t leafk_backward_workspace_bytes(const leafk_config* cfg, int B, int T) { return bwd_workspace_bytes(cfg, B, T); }
 
 int leafk_backward(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,

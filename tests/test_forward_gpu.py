@@ -254,3 +254,32 @@ def test_maximum_batch_config3_size_properties():
     assert tuple(big.shape) == (1024, 80, 100)
     assert torch.equal(big[idx], small)
     assert torch.isfinite(big).all()
+
+
+@pytest.mark.parametrize("depth,dtype", [(1, torch.float32), (2, torch.float32), (3, torch.float32), (2, torch.int16)])
+def test_host_pipeline_batches_in_flight(depth, dtype):
+    """HostPipeline (leafk_forward_host_async): several batches in flight, every result identical to the
+    device-resident forward of the same input, whatever the submit/collect interleaving."""
+    import leaf_pytorch_b200 as L
+    case, x, prm, z = load_golden("cfg1_default")
+    fe = build(case, prm, "auto")
+    B, T = 6, 9000
+    g = torch.Generator().manual_seed(21)
+    xs = [(torch.randn(B, 1, T, generator=g).clamp_(-4, 4) / 4) for _ in range(7)]
+    if dtype == torch.int16:
+        xs = [(v * 32767).round().to(torch.int16) for v in xs]
+    with torch.no_grad():
+        want = [fe(v.cuda()).cpu() for v in xs]
+    hosts = [v.pin_memory() for v in xs]
+    pipe = L.HostPipeline(fe, B, T, depth=depth, n_slices=3, input_dtype=dtype)
+    tickets, got = [], []
+    for i, h in enumerate(hosts):
+        tickets.append(pipe.submit(h))
+        if len(tickets) == depth:                         # keep `depth` batches in flight
+            got.append(pipe.result(tickets.pop(0)).clone())
+    while tickets:
+        got.append(pipe.result(tickets.pop(0)).clone())
+    pipe.close()
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
