@@ -283,3 +283,19 @@ def test_host_pipeline_batches_in_flight(depth, dtype):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_benchmark_config_subsample_against_oracle():
+    """BASELINE configs[1] exactly as bench.py runs it (256 x 1 s, default Leaf, bench's synthetic generator): a
+    subsample of the clips is recomputed by the CPU oracle and must agree within the parity tolerance."""
+    import leaf_pytorch_b200 as L
+    from oracle import leaf_oracle as O
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(256, 1, 16000, generator=g).clamp_(-4, 4) / 4
+    fe = L.Leaf().cuda()
+    with torch.no_grad():
+        out = fe(x.cuda()).cpu()
+    idx = [0, 37, 101, 128, 200, 255]
+    prm = O.params_from_state_dict({k: v.detach().cpu() for k, v in fe.state_dict().items()})
+    ref = O.forward_f32(x[idx], prm, 401, 160).numpy()
+    assert_close(out[idx].numpy(), ref, "cfg2 subsample vs oracle")
