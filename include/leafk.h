@@ -48,6 +48,12 @@ extern "C" {
  * 27 % less backward time. */
 #define LEAFK_BWD_2PRODUCT 16
 
+/* Flag OR-ed into `algo`, forward tensor-core kernel only (testing / A-B measurement).  By default the kernel
+ * skips, per k-step of 16 taps, the filters whose Gaussian envelope has decayed below exp(-5.5^2/2) = 2.7e-7 of its
+ * peak over the whole k-step (|tau| > ceil(5.5 sigma)): the rounding level of the fp16 hi/lo split itself.  With
+ * this flag every filter runs over all taps. */
+#define LEAFK_TC_NOPRUNE 32
+
 /* Learnable parameters of the frontend, in the reference's state_dict layout.
  *   kernel   (F,2)  _complex_conv._kernel      reference convolution.py:58
  *   pool_w   (F)    _pooling.weights (1,1,F,1) reference pooling.py:18-20

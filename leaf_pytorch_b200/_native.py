@@ -14,7 +14,8 @@ import threading
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libleafk.so")
 
 ALGO_AUTO, ALGO_FP32, ALGO_TC = 0, 1, 2
-ALGOS = {"auto": ALGO_AUTO, "fp32": ALGO_FP32, "tc": ALGO_TC}
+TC_NOPRUNE = 32        # LEAFK_TC_NOPRUNE: every filter over all taps (no support pruning of the k-steps)
+ALGOS = {"auto": ALGO_AUTO, "fp32": ALGO_FP32, "tc": ALGO_TC, "tc_full": ALGO_TC | TC_NOPRUNE}
 BWD_2PRODUCT = 16
 
 SYMBOLS = (

@@ -29,23 +29,83 @@ struct BankConsts {
   float pool_lo;    // 2/K                    impulse_responses.py:75
 };
 
+// Width-sorted channel order and per-k-step active counts of the pruned tensor-core layout
+// (k1_tc_layout.cuh, "SUPPORT PRUNING").  Every block recomputes the (tiny) sort redundantly so that one
+// launch suffices: sm_key[f'] = clamped sigma (or -1 for padding filters), sm_pos[f'] = rank of f' in
+// ascending (key, index) order, sm_na[s] = active channels of THIS filter's group at k-step s.
+struct TcPrune {
+  int* perm;          // [groups][FG] (group, slot) -> filter index (>= F: padding)
+  int* zones;         // [groups][tc::ZONE_INTS]: {lo_L, hi_L} = k-steps with >= 16 L active channels, L = 1..CG/16
+  float c;            // support radius in sigmas; <= 0: no pruning
+};
+
 __global__ void __launch_bounds__(128)
 k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool_w, BankConsts bc,
                 int F, int K, int Kp, int C2p, float* __restrict__ cprm, float* __restrict__ w32,
-                float* __restrict__ g32, uint8_t* __restrict__ w16, int tc_cg, int tc_groups) {
+                float* __restrict__ g32, uint8_t* __restrict__ w16, int tc_cg, int tc_groups, TcPrune pr) {
+  extern __shared__ float k0_smem[];
   const int f = blockIdx.x;                 // filter (or a zero-padding channel pair when f >= F)
   const size_t grp_bytes = tc::b_group_bytes(tc_cg, Kp);
+  const int FG = tc_cg / 2, Fp = FG * tc_groups, ks = Kp / tc::KSTEP;
+  float* sm_key = k0_smem;
+  int* sm_pos = reinterpret_cast<int*>(k0_smem + Fp);
+  int* sm_na = sm_pos + Fp;
+  int my_pos = 0;
+  if (w16 != nullptr) {
+    for (int i = threadIdx.x; i < Fp; i += blockDim.x)
+      sm_key[i] = (i < F) ? fminf(fmaxf(kernel[2 * i + 1], bc.sigma_lo), bc.sigma_hi) : -1.0f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < Fp; i += blockDim.x) {
+      const float ki = sm_key[i];
+      int r = 0;
+      for (int j = 0; j < Fp; ++j) {
+        const float kj = sm_key[j];
+        r += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
+      }
+      sm_pos[i] = r;
+    }
+    __syncthreads();
+    my_pos = sm_pos[f < Fp ? f : 0];
+    const int my_grp = tc::group_of(my_pos, tc_groups);
+    for (int s = threadIdx.x; s < ks; s += blockDim.x) {
+      int cnt = 0;
+      for (int j = 0; j < Fp; ++j)
+        cnt += (tc::group_of(sm_pos[j], tc_groups) == my_grp && tc::kstep_active(sm_key[j], pr.c, s, K)) ? 1 : 0;
+      int nf = (cnt + 7) / 8 * 8;
+      if (nf > FG || s == tc::first_kstep(Kp)) nf = FG;
+      sm_na[s] = 2 * nf;
+    }
+    __syncthreads();
+    if (f < Fp) {
+      if (threadIdx.x == 0) pr.perm[my_grp * FG + tc::slot_of(my_pos, tc_groups)] = f;
+      if (tc::slot_of(my_pos, tc_groups) == 0 && threadIdx.x < tc_cg / 16) {     // the group's first filter publishes the zone table
+        const int L = threadIdx.x + 1;
+        int lo = ks, hi = -1;
+        for (int s = 0; s < ks; ++s)
+          if (sm_na[s] >= 16 * L) { lo = s < lo ? s : lo; hi = s; }
+        pr.zones[my_grp * tc::ZONE_INTS + 2 * (L - 1)] = lo;
+        pr.zones[my_grp * tc::ZONE_INTS + 2 * (L - 1) + 1] = hi;
+      }
+    }
+  }
+  // tensor-core image: taps of sorted channel c = 2*j + q of group grp, only where the k-step keeps the channel
+  auto store_tc = [&](int k, int q, float scaled) {
+    const int grp = tc::group_of(my_pos, tc_groups), j = tc::slot_of(my_pos, tc_groups), c = 2 * j + q;
+    const int na = sm_na[k / tc::KSTEP];
+    if (c < tc_cg - na) return;                        // outside the active suffix: never read by the MMAs
+    uint8_t* gb = w16 + (size_t)grp * grp_bytes;
+    const __half hi = __float2half_rn(scaled);
+    const __half lo = __float2half_rn(scaled - __half2float(hi));
+    *reinterpret_cast<__half*>(gb + tc::p_hi_main(tc_cg, Kp, c, k)) = hi;
+    *reinterpret_cast<__half*>(gb + tc::p_lo_main(tc_cg, Kp, c, na, k)) = lo;
+    *reinterpret_cast<__half*>(gb + tc::p_hi_corr(tc_cg, Kp, c, na, k)) = hi;
+  };
   if (f >= F) {                             // padded channels: zero taps in both layouts
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
-      for (int c = 2 * f; c < 2 * f + 2; ++c) {
+      for (int q = 0; q < 2; ++q) {
+        const int c = 2 * f + q;
         if (c < C2p) w32[(size_t)k * C2p + c] = 0.f;
-        if (w16 != nullptr && c < tc_cg * tc_groups) {
-          uint8_t* gb = w16 + (size_t)(c / tc_cg) * grp_bytes;
-          const __half z = __float2half_rn(0.f);
-          *reinterpret_cast<__half*>(gb + tc::g_hi_main(tc_cg, Kp, c % tc_cg, k)) = z;
-          *reinterpret_cast<__half*>(gb + tc::g_lo_main(tc_cg, Kp, c % tc_cg, k)) = z;
-          *reinterpret_cast<__half*>(gb + tc::g_hi_corr(tc_cg, Kp, c % tc_cg, k)) = z;
-        }
+        if (w16 != nullptr && f < Fp) store_tc(k, q, 0.f);
       }
     }
     return;
@@ -94,18 +154,8 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
     w32[(size_t)k * C2p + 2 * f + 1] = wi;
     if (w16 != nullptr) {
       // hi/lo fp16 split of the scaled taps, stored in the CTA-pair regions of the channel's group
-      // (k1_tc_layout.cuh): hi -> R1 of CTA0 and R2 of CTA (c / (CG/2)); lo -> R1 of CTA1
-      const float sc[2] = {ldexpf(wr, wshift), ldexpf(wi, wshift)};
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int c = 2 * f + q;
-        uint8_t* gb = w16 + (size_t)(c / tc_cg) * grp_bytes;
-        const __half hi = __float2half_rn(sc[q]);
-        const __half lo = __float2half_rn(sc[q] - __half2float(hi));
-        *reinterpret_cast<__half*>(gb + tc::g_hi_main(tc_cg, Kp, c % tc_cg, k)) = hi;
-        *reinterpret_cast<__half*>(gb + tc::g_lo_main(tc_cg, Kp, c % tc_cg, k)) = lo;
-        *reinterpret_cast<__half*>(gb + tc::g_hi_corr(tc_cg, Kp, c % tc_cg, k)) = hi;
-      }
+      store_tc(k, 0, ldexpf(wr, wshift));
+      store_tc(k, 1, ldexpf(wi, wshift));
     }
   }
 }
@@ -230,12 +280,15 @@ void launch_k0_bwd(const float* kernel, const float* pool_w, int F, int K, int K
 }
 
 void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
-               float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, cudaStream_t stream) {
+               float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, int* tc_perm, int* tc_zones,
+               float prune_c, cudaStream_t stream) {
   const BankConsts bc = make_consts(K);
   int nblk = C2p / 2;
-  if (w16 != nullptr && tc_cg * tc_groups / 2 > nblk) nblk = tc_cg * tc_groups / 2;
-  k0_banks_kernel<<<nblk, 128, 0, stream>>>(kernel, pool_w, bc, F, K, Kp, C2p, cprm, w32, g32, w16, tc_cg,
-                                            tc_groups);
+  const int Fp = tc_cg * tc_groups / 2;
+  if (w16 != nullptr && Fp > nblk) nblk = Fp;
+  const size_t smem = (w16 != nullptr) ? sizeof(float) * (2 * (size_t)Fp + Kp / tc::KSTEP) : 0;
+  k0_banks_kernel<<<nblk, 128, smem, stream>>>(kernel, pool_w, bc, F, K, Kp, C2p, cprm, w32, g32, w16, tc_cg,
+                                               tc_groups, TcPrune{tc_perm, tc_zones, prune_c});
 }
 
 }  // namespace leafk

@@ -101,6 +101,13 @@ struct TcReady {
   long long* perf;      // optional: CTA 0 stores {SM cycles, nanoseconds} of its lifetime (effective SM clock)
 };
 
+// Forward only: the width-sorted channel order and the per-k-step active channel counts written by k0
+// (k1_tc_layout.cuh, "SUPPORT PRUNING").
+struct TcMap {
+  const int* perm;      // [n_groups * CG/2] sorted position -> filter index (>= F: padding)
+  const int* zones;     // [n_groups][tc::ZONE_INTS] {lo_L, hi_L} for L = 1..CG/16: k-steps with >= 16 L active channels
+};
+
 struct TcBwdArgs {
   const float* dpT;     // (B, N, F) gradient w.r.t. the floored pooled energies, frame-major
   const float* bprm;    // (Fpad, 8): [0] pooling exp2 coefficient, [1..3] power-of-two shifts of the y,z,v banks
@@ -110,6 +117,37 @@ struct TcBwdArgs {
                         //    (zero-mean, averages out over the B*T terms of a gradient), the banks keep hi+lo
 };
 
+// ---- pruned MMA issue (forward) ------------------------------------------------------------------------------
+// The active channel count na(s) is unimodal in the k-step s (nested, centred supports), so the k-steps split into
+// at most 2*CG/16 - 1 ZONES of constant na: level L (na >= 16 L) is active on the k-step interval [lo_L, hi_L],
+// intervals nested.  k0 publishes the bounds; the issuing warp makes them warp-uniform registers (redux) and runs
+// one short loop per zone with NA a compile-time constant: running descriptors advanced by immediates, i.e. two
+// 64-bit uniform adds per MMA like the unpruned loop.  (Measured alternatives: a per-k-step table in shared memory
+// cost ~18 R2UR and 190 cycles per k-step, a per-k-step switch with immediate offsets -- jump tables -- 340.)
+template <int CG, int NA>
+__device__ __forceinline__ void issue_zone(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b1, uint64_t b2, int s0,
+                                           int s1, uint32_t accumulate_first) {
+  uint64_t ah = a_hi + (uint64_t)(2 * s0), al = a_lo + (uint64_t)(2 * s0);
+  uint64_t bb1 = b1 + (uint64_t)(s0 * 2 * CG + (CG - NA)), bb2 = b2 + (uint64_t)(s0 * CG + (CG - NA) / 2);
+  const uint32_t dd = d + (uint32_t)(CG - NA);
+#pragma unroll 1
+  for (int s = s0; s < s1; ++s) {
+    mma_f16_ss_pair(dd, ah, bb1, idesc_f16(256, 2 * NA), (s > s0) ? 1u : accumulate_first);
+    mma_f16_ss_pair(dd, al, bb2, idesc_f16(256, NA), 1);
+    ah += 2; al += 2; bb1 += (uint64_t)(2 * CG); bb2 += (uint64_t)CG;
+  }
+}
+// zones outside the centre one, levels L = LV .. 1 (rising side [lo_L, lo_{L+1}), falling side (hi_{L+1}, hi_L])
+template <int CG, int LV>
+__device__ __forceinline__ void issue_outer_zones(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b1, uint64_t b2,
+                                                  const int* zlo, const int* zhi) {
+  if constexpr (LV >= 1) {
+    issue_zone<CG, 16 * LV>(d, a_hi, a_lo, b1, b2, zlo[LV - 1], zlo[LV], 1);
+    issue_zone<CG, 16 * LV>(d, a_hi, a_lo, b1, b2, zhi[LV] + 1, zhi[LV - 1] + 1, 1);
+    issue_outer_zones<CG, LV - 1>(d, a_hi, a_lo, b1, b2, zlo, zhi);
+  }
+}
+
 // KS > 0: number of k-steps known at compile time (26 for the default 401-tap window): the MMA issue loop is
 // fully unrolled with immediate descriptor offsets -- with a runtime trip count the per-iteration descriptor
 // arithmetic made the single issuing lane the bottleneck (149 cycles per k-step measured vs 124 issued tight).
@@ -117,7 +155,7 @@ template <int CG, int NSLOT, int MODE, int KS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1)
 k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restrict__ w16,
              const float* __restrict__ cprm, float* __restrict__ ppart, int n_groups, const TcBwdArgs ba,
-             const TcReady rdy) {
+             const TcReady rdy, const TcMap tm) {
   using namespace tc;
   constexpr int NB = 2 * CG;                 // accumulator columns per stage (hi | lo products)
   constexpr int NST = (512 / NB) > 4 ? 4 : (512 / NB);
@@ -247,6 +285,18 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       const uint64_t b1_desc0 = smem_desc(w_base, CG * 16, 128);                               // R1: CG rows per CTA
       const uint64_t b2_desc0 = smem_desc(w_base + (uint32_t)r1_bytes(CG, g.Kp), (CG / 2) * 16, 128);  // R2: CG/2 rows
       const uint64_t b1_step = (uint64_t)((CG * 32) >> 4), b2_step = (uint64_t)(((CG / 2) * 32) >> 4);
+      // Forward: zone bounds of this channel group (k0's support pruning), made warp-uniform with a redux so
+      // that the zone loops run on uniform registers.
+      constexpr int LMAX = CG / 16;
+      int zlo[LMAX], zhi[LMAX];
+      if constexpr (MODE == 0) {
+        const int* z = tm.zones + (size_t)grp * tc::ZONE_INTS;
+#pragma unroll
+        for (int L = 0; L < LMAX; ++L) {
+          zlo[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 2 * L));
+          zhi[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 2 * L + 1));
+        }
+      }
       int it = 0;
       for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
 #pragma unroll 1
@@ -259,7 +309,15 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
           const uint32_t d = tmem + (uint32_t)(st * NB);
           const uint64_t a_hi = smem_desc(a_base + (uint32_t)((2 * p) * sp.acb), 16, 128);
           const uint64_t a_lo = smem_desc(a_base + (uint32_t)((2 * p + 1) * sp.acb), 16, 128);
-          if (leader) {
+          if constexpr (MODE == 0) {
+            if (leader) {
+              // centre zone first (every channel; its first MMA initialises all 2*CG accumulator columns)
+              issue_zone<CG, CG>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo[LMAX - 1], zhi[LMAX - 1] + 1, 0);
+              issue_outer_zones<CG, LMAX - 1>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo, zhi);
+              mma_commit_pair(&misc->a_empty[p]);
+              mma_commit_pair(&misc->acc_full[st]);
+            }
+          } else if (leader) {
             if (MODE == 1 && ba.skip_xlo) {
 #pragma unroll 4
               for (int ks = 0; ks < ksteps; ++ks)
@@ -289,10 +347,14 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
     const int e = warp, q = e & 3, hh = e >> 2;
     const int etid = tid;                               // 0..255
     const int m = 32 * q + lane;                        // accumulator row
-    const int fbase = grp * (CG / 2) + hh * FPT;        // first filter of this thread
+    // this thread's filters: sorted positions hh*FPT + i of the group; perm gives the filter they belong to
+    const int* gperm = tm.perm + (size_t)grp * (CG / 2);
     float pa[FPT];
 #pragma unroll
-    for (int i = 0; i < FPT; ++i) pa[i] = (fbase + i < g.F) ? __ldg(cprm + (size_t)(fbase + i) * 8 + CP_POOLA) : -1.0f;
+    for (int i = 0; i < FPT; ++i) {
+      const int f = __ldg(gperm + hh * FPT + i);
+      pa[i] = (f < g.F) ? __ldg(cprm + (size_t)f * 8 + CP_POOLA) : -1.0f;
+    }
     const float centre = 0.5f * (float)(g.K - 1);
     const int n_last = g.n_begin + g.n_count - 1;
     int it = 0;
@@ -328,13 +390,16 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         mbar_wait(&misc->acc_full[st], (uint32_t)((gp / NST) & 1));
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + hh * (CG / 2));
+        const uint32_t tlo = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + 2 * CG - 8 - hh * (CG / 2));
 #pragma unroll
         for (int c = 0; c < FPT / 4; ++c) {
+          // hi products of the 4 filters at columns hh*CG/2 + 8c ..; their lo products sit in the mirrored
+          // 8-column block of the lo half, filters in reverse order (k1_tc_layout.cuh)
           float ym[8], yc[8];
-          tmem_ld8x2_sync(taddr + 8 * c, taddr + CG + 8 * c, ym, yc);
+          tmem_ld8x2_sync(taddr + 8 * c, tlo - 8 * c, ym, yc);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float re = ym[2 * i] + yc[2 * i], im = ym[2 * i + 1] + yc[2 * i + 1];
+            const float re = ym[2 * i] + yc[2 * (3 - i)], im = ym[2 * i + 1] + yc[2 * (3 - i) + 1];
             const float en = fmaf(re, re, im * im);
 #pragma unroll
             for (int j = 0; j < NSLOT; ++j)
@@ -375,7 +440,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       for (int idx = etid; idx < g.SL * (CG / 2); idx += EPI_WARPS * 32) {
         const int fl = idx / g.SL, slot = idx % g.SL;       // (filter, slot) layout, slot fastest
         const int h2 = fl / FPT, fi = fl % FPT;
-        const int f = grp * (CG / 2) + fl;
+        const int f = __ldg(gperm + fl);                    // sorted position -> filter
         if (valid && f < g.F) {
           float s = 0.f;
 #pragma unroll
@@ -531,20 +596,17 @@ bool k1_tc_supported(const Geom& g, const char** why) {
 
 template <int CG, int NSLOT, int KS>
 static cudaError_t launch_inst_ks(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
-                                  int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy) {
+                                  int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy, const TcMap& tm) {
   cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   TcBwdArgs none{nullptr, nullptr, nullptr, 0, 0};
-  k1_tc_kernel<CG, NSLOT, 0, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups, none, rdy);
+  k1_tc_kernel<CG, NSLOT, 0, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups, none, rdy, tm);
   return cudaGetLastError();
 }
 template <int CG, int NSLOT>
 static cudaError_t launch_inst(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
-                               int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy) {
-  if constexpr (NSLOT == 3 && (CG == 80 || CG == 64)) {      // the shipped configs (F=40/80, F=64) at 401 taps
-    if (g.Kp == 26 * tc::KSTEP) return launch_inst_ks<CG, NSLOT, 26>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy);
-  }
-  return launch_inst_ks<CG, NSLOT, 0>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy);
+                               int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy, const TcMap& tm) {
+  return launch_inst_ks<CG, NSLOT, 0>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy, tm);
 }
 
 template <int CG, int NSLOT, int KS>
@@ -554,7 +616,7 @@ static cudaError_t launch_bwd_inst_ks(const Geom& g, const float* x, const uint8
   cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 1, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   k1_tc_kernel<CG, NSLOT, 1, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, nullptr, nullptr, n_groups, ba,
-                                                                       TcReady{nullptr, 1, nullptr});
+                                                                       TcReady{nullptr, 1, nullptr}, TcMap{nullptr, nullptr});
   return cudaGetLastError();
 }
 template <int CG, int NSLOT>
@@ -600,16 +662,17 @@ cudaError_t launch_k1_tc_bwd(const Geom& g, const float* x, const uint8_t* w16b,
 
 template <int CG>
 static cudaError_t launch_cg(int nslot, const Geom& g, const float* x, const uint8_t* w16, const float* cprm,
-                             float* ppart, int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy) {
-  if (nslot <= 3) return launch_inst<CG, 3>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy);
-  if constexpr (CG <= 64) return launch_inst<CG, 5>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy);
+                             float* ppart, int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy, const TcMap& tm) {
+  if (nslot <= 3) return launch_inst<CG, 3>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy, tm);
+  if constexpr (CG <= 64) return launch_inst<CG, 5>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy, tm);
   return cudaErrorNotSupported;
 }
 
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
-                         int tc_cg, int tc_groups, cudaStream_t stream, const int* ready, int clips_per_flag,
-                         long long* perf) {
+                         int tc_cg, int tc_groups, const int* tc_perm, const int* tc_zones, cudaStream_t stream,
+                         const int* ready, int clips_per_flag, long long* perf) {
   const TcReady rdy{ready, clips_per_flag < 1 ? 1 : clips_per_flag, perf};
+  const TcMap tm{tc_perm, tc_zones};
   cudaError_t err;
   const int n_sm = sm_count(&err);
   if (err != cudaSuccess) return err;
@@ -617,12 +680,12 @@ cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, cons
   const int nslot = tc::slots_per_thread(g.K, g.H);
   const int smem = tc::smem_plan(tc_cg, g.Kp, g.SL).total;
   switch (tc_cg) {
-    case 16: return launch_cg<16>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
-    case 32: return launch_cg<32>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
-    case 48: return launch_cg<48>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
-    case 64: return launch_cg<64>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
-    case 80: return launch_cg<80>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
-    case 96: return launch_cg<96>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy);
+    case 16: return launch_cg<16>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
+    case 32: return launch_cg<32>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
+    case 48: return launch_cg<48>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
+    case 64: return launch_cg<64>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
+    case 80: return launch_cg<80>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
+    case 96: return launch_cg<96>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
     default: return cudaErrorNotSupported;
   }
 }

@@ -15,6 +15,26 @@
 // (Halving the B rows each CTA feeds its tensor core is what takes the shared-memory pipe off the
 // critical path: 94 operand wavefronts per k-step instead of 124, ncu r01.)
 //
+//
+// SUPPORT PRUNING (forward bank only).  A Gabor filter's taps beyond |tau| > R_f = ceil(c * sigma_f) are below
+// exp(-c^2/2) of its peak (c = 5.5: 2.7e-7, the level of the fp16 hi/lo split itself), so k-steps whose 16 taps
+// all lie outside [-R_f, R_f] contribute nothing for filter f.  k0 sorts the filters by width (ascending; padding
+// filters first), deals the sorted list round-robin to the channel groups, and for every (group, k-step) finds
+//   na[g][s] = 2 * (number of filters of the group, rounded up to 8, that are still inside their support)
+// -- the active channels are always the LAST na columns of the group's sorted order, and na is unimodal in s, so
+// it is published as nested k-step intervals: level L (na >= 16 L) is active on [lo_L, hi_L], L = 1..CG/16.  The MMAs of k-step s then
+// run with N = 2*na (main) and N = na (corr) and accumulate into columns [CG-na, CG+na) / [CG-na, CG):
+//   main, CTA0 rows [CG-na, CG)          hi of sorted channels CG-na .. CG-1          (row = channel)
+//   main, CTA1 rows [CG-na, CG)          lo halves in REVERSED filter order: D column CG+i holds the lo product
+//                                        of channel lo_channel(i) = 2*(FG-1 - i/2) + i%2, stored at row CG-na+i,
+//                                        so the lo product of a channel lands in the same column for every na
+//   corr, CTA0 rows [CG/2-na/2, CG/2)    hi of channels CG-na .. CG-na/2-1            (row = c - CG/2 + na/2)
+//   corr, CTA1 rows [CG/2-na/2, CG/2)    hi of channels CG-na/2 .. CG-1               (row = c - CG/2)
+// (one descriptor start offset serves both CTAs of the pair).  The middle k-step first_kstep(Kp) (|tau| <= 16 for
+// some tap: inside every real filter's support) is always run with na = CG and is issued first with
+// accumulate = 0, so every accumulator column is initialised.  With na = CG
+// everywhere this is the unpruned layout up to the order of the lo columns.
+//
 // A operand = NOT materialised.  For phase p (0..7) a linear fp16 copy of the scaled sample window,
 // shifted by p samples, sits in shared memory: copy_p[i] = x~[ts - padL + p + i].  The descriptor
 // {start = copy_p + s*32 B, LBO = 16 B, SBO = 128 B} makes row m of the 128x16 operand read
@@ -50,12 +70,43 @@ __host__ __device__ inline size_t g_hi_corr(int CG, int Kp, int c, int k) {
   return 2 * r1_bytes(CG, Kp) + (size_t)(c / h) * r2_bytes(CG, Kp) + region_offset(h, c % h, k);
 }
 
+// ---- pruned forward layout: byte offsets inside a group's global image for sorted channel c = 2*j + ri -------
+// (FG = CG/2 filters per group, j = sorted position in the group, na = active channels of the k-step, k = tap)
+__host__ __device__ inline size_t p_hi_main(int CG, int Kp, int c, int k) { return region_offset(CG, c, k); }
+__host__ __device__ inline size_t p_lo_main(int CG, int Kp, int c, int na, int k) {
+  const int FG = CG / 2, j = c >> 1, ri = c & 1;
+  const int i = 2 * (FG - 1 - j) + ri;                      // lo column (relative to CG) of this channel
+  return r1_bytes(CG, Kp) + region_offset(CG, CG - na + i, k);
+}
+__host__ __device__ inline size_t p_hi_corr(int CG, int Kp, int c, int na, int k) {
+  const int h = CG / 2;
+  if (c < CG - na / 2) return 2 * r1_bytes(CG, Kp) + region_offset(h, c - h + na / 2, k);
+  return 2 * r1_bytes(CG, Kp) + r2_bytes(CG, Kp) + region_offset(h, c - h, k);
+}
+// inside the support of a filter of width sigma?  (k-step s of a K-tap window, prune factor c; c <= 0: always)
+__host__ __device__ inline bool kstep_active(float sigma, float c, int s, int K) {
+  if (!(c > 0.f)) return true;
+  if (sigma < 0.f) return false;                            // padding filter
+  const int k0 = s * KSTEP, k1 = (k0 + KSTEP - 1 < K - 1) ? k0 + KSTEP - 1 : K - 1, kc = K / 2;
+  const int dmin = (kc < k0) ? k0 - kc : ((kc > k1) ? kc - k1 : 0);
+  return (float)dmin <= ceilf(c * sigma);
+}
+constexpr float PRUNE_C = 5.5f;      // default support radius in units of sigma
+// k-step the forward kernel issues first (accumulate = 0): k0 keeps every channel of every group active there
+__host__ __device__ constexpr int first_kstep(int Kp) { return (Kp / KSTEP - 1) / 2; }
+// width rank (ascending) -> channel group and slot inside it: the ranks are DEALT to the groups round-robin, so
+// every group holds the same mix of narrow and wide filters (same pruning profile, same cost per tile) and the
+// slots of a group are still in ascending width
+__host__ __device__ inline int group_of(int rank, int n_groups) { return rank % n_groups; }
+__host__ __device__ inline int slot_of(int rank, int n_groups) { return rank / n_groups; }
+constexpr int ZONE_INTS = 16;       // ints per channel group in the zone table: {lo_L, hi_L}, L = 1..CG/16 <= 6
+
 // Byte offsets of the kernel's dynamic shared memory regions.
 struct SmemPlan {
   int CL;          // halves per shifted copy: 8*127 + Kp
   int LX;          // samples staged per tile: CL + 8
   int acb;         // bytes per copy
-  int off_w, off_acopy, off_st32, off_sth, off_stl, off_pw, off_misc, total;
+  int off_w, off_acopy, off_st32, off_sth, off_stl, off_pw, off_prog, off_misc, total;
 };
 
 // mode 0: forward (pooling partial buffers), mode 1: backward (small reduction scratch instead)
@@ -71,7 +122,8 @@ __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode =
   s.off_sth = off;    off += (s.LX * 2 + 15) / 16 * 16;
   s.off_stl = off;    off += (s.LX * 2 + 15) / 16 * 16;
   s.off_pw = off;     off += (mode == 0) ? 2 * 8 * SL * (CG / 4) * 4 : 8 * 32 * 4;
-  s.off_misc = (off + 15) / 16 * 16;
+  s.off_prog = (off + 15) / 16 * 16;
+  s.off_misc = s.off_prog;
   s.total = s.off_misc + 512;
   return s;
 }

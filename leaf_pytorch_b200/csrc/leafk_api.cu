@@ -12,7 +12,8 @@
 namespace leafk {
 // k0_banks.cu
 void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
-               float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, cudaStream_t stream);
+               float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, int* tc_perm, int* tc_zones,
+               float prune_c, cudaStream_t stream);
 // k1_fp32.cu
 cudaError_t launch_k1_fp32(const Geom& g, const float* x, const float* w32, const float* g32,
                            float* ppart, cudaStream_t stream);
@@ -20,8 +21,8 @@ constexpr int F32_TILE = 512;
 // k1_tc.cu
 bool k1_tc_supported(const Geom& g, const char** why);
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm,
-                         float* ppart, int tc_cg, int tc_groups, cudaStream_t stream, const int* ready,
-                         int clips_per_flag, long long* perf);
+                         float* ppart, int tc_cg, int tc_groups, const int* tc_perm, const int* tc_zones,
+                         cudaStream_t stream, const int* ready, int clips_per_flag, long long* perf);
 constexpr int TC_TILE = 1024;
 // k2_pcen.cu
 cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cudaStream_t stream);
@@ -115,6 +116,7 @@ static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace
   w->off_w32 = off;  off += align256(sizeof(float) * (size_t)g.Kp * g.C2p);
   w->off_g32 = off;  off += align256(sizeof(float) * (size_t)g.K * g.F);
   w->off_w16 = off;  off += align256(tc::b_group_bytes(*tc_cg, g.Kp) * (size_t)*tc_groups);
+  w->off_tcmap = off; off += align256(sizeof(int) * (size_t)*tc_groups * (*tc_cg / 2 + tc::ZONE_INTS));
   w->off_ppart = off;
   const int sl32 = (F32_TILE + g.K - 2) / g.H + 1, sltc = (TC_TILE + g.K - 2) / g.H + 1;
   size_t a = (size_t)max_tiles_fp32 * sl32, b = (size_t)max_tiles_tc * sltc;
@@ -197,10 +199,13 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   float* g32 = (float*)(base + w.off_g32);
   uint8_t* w16 = base + w.off_w16;
   float* ppart = (float*)(base + w.off_ppart);
+  int* tc_perm = (int*)(base + w.off_tcmap);
+  int* tc_zones = tc_perm + (size_t)tc_groups * (tc_cg / 2);
+  const float prune_c = (cfg->algo & LEAFK_TC_NOPRUNE) ? 0.f : tc::PRUNE_C;
 
   prof_mark(0, stream);
   launch_k0(prm->kernel, prm->pool_w, g.F, g.K, g.Kp, g.C2p, cprm, w32, g32,
-            algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, stream);
+            algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, tc_perm, tc_zones, prune_c, stream);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0 launch: %s", cudaGetErrorString(err));
   prof_mark(1, stream);
@@ -208,8 +213,8 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   if (flags_out) *flags_out = flags;
   if (algo_out) *algo_out = algo;
   if (algo == LEAFK_ALGO_TC)
-    err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, stream, clips_per_flag > 0 ? flags : nullptr,
-                       clips_per_flag, g_prof_on ? (long long*)(flags + 32) : nullptr);
+    err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, tc_perm, tc_zones, stream,
+                       clips_per_flag > 0 ? flags : nullptr, clips_per_flag, g_prof_on ? (long long*)(flags + 32) : nullptr);
   else
     err = launch_k1_fp32(g, x_win, w32, g32, ppart, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k1 launch: %s", cudaGetErrorString(err));

@@ -15,7 +15,7 @@ from tests.util import load_golden, scaled_err
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL = 1e-4, 1e-5
-ALGOS = ["fp32", "tc"]
+ALGOS = ["fp32", "tc", "tc_full"]     # tc: support-pruned k-steps (default), tc_full: every tap
 SMALL = [c.name for c in CASES if c.T <= 20000 and not c.grads]
 
 
@@ -34,7 +34,7 @@ def build(case, prm, algo, device="cuda"):
 
 
 def algo_available(case, algo):
-    if algo != "tc":
+    if not algo.startswith("tc"):
         return True
     import leaf_pytorch_b200.functional as LF
     return LF.tc_supported(case.F, case.K, case.H)

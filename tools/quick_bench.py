@@ -38,10 +38,12 @@ def main():
             ms = timeit(lambda: fe(x))
         print(f"algo={algo:5s} F={F} B={B} T={T}: {ms:8.3f} ms/forward  {B*T/16000/(ms*1e-3):12.0f} audio-s/s  "
               f"{2*2*F*fe.spec.K*T*B/(ms*1e-3)/1e12:7.2f} TFLOP/s(alg)")
-    if "fp32" in outs and "tc" in outs:
-        a, b = outs["fp32"].cpu().numpy(), outs["tc"].cpu().numpy()
-        d = np.abs(a - b)
-        print("tc vs fp32: max|d| %.3e  max rel %.3e  finite=%s" % (d.max(), (d / np.maximum(np.abs(a), 1e-3)).max(), np.isfinite(b).all()))
+    names = list(outs)
+    for i in range(len(names)):
+        for j in range(i + 1, len(names)):
+            a, b = outs[names[i]].cpu().numpy(), outs[names[j]].cpu().numpy()
+            d = np.abs(a - b)
+            print("%s vs %s: max|d| %.3e  max rel %.3e  finite=%s" % (names[j], names[i], d.max(), (d / np.maximum(np.abs(a), 1e-3)).max(), np.isfinite(b).all()))
 
 
 if __name__ == "__main__":
