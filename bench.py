@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--algo", default="auto", choices=["auto", "tc", "fp32"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "tc", "tc_full", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -274,11 +274,13 @@ def main():
         n_prof, ms_k0, ms_k1, ms_k2 = LF.profile_end()
         # effective SM clock of K1: cycles and nanoseconds counted inside the kernel, right after a hot loop
         k1_cyc = k1_ns = 0
+        sched = None
         if args.algo != "fp32" and LF.tc_supported(F, K, H):
             for i in range(steps):
                 fe(xs[i % N_ROTATE])
             prm_t = [None if q is None else q.detach() for q in fe._param_tuple()]
             k1_cyc, k1_ns = LF.k1_clock_probe(fe.spec, xs[0], *prm_t)
+            sched = LF.tc_schedule(fe.spec, xs[0], *prm_t)
 
     times = torch.tensor([ms_total, e2e_s * 1e3, pcm_s * 1e3, sync_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -294,9 +296,11 @@ def main():
         bytes_alg = 4.0 * B * T + 4.0 * B * F * n_frames + 32.0 * F
         k1_s = ms_k1 * 1e-3
         algo_used = "tc" if (args.algo != "fp32" and LF.tc_supported(F, K, H)) else "fp32"
-        exec_mult = 3.0 * ((K + 15) // 16 * 16) / K if algo_used == "tc" else 1.0
+        algo_name = ("tc_full" if args.algo == "tc_full" else "tc") if algo_used == "tc" else "fp32"
+        exec_frac = sched["executed_fraction"] if sched else 1.0   # support pruning: share of (channel, k-step) pairs run
+        exec_mult = 3.0 * ((K + 15) // 16 * 16) / K * exec_frac if algo_used == "tc" else 1.0
         roofline = {
-            "kernel": "k1_tc_kernel<80,3,0,26> on CTA pairs (Gabor Toeplitz GEMM + modulus + pooling partials)" if algo_used == "tc"
+            "kernel": "k1_tc_kernel<80,3,0,0> on CTA pairs (Gabor Toeplitz GEMM + modulus + pooling partials)" if algo_used == "tc"
             else "k1_fp32_kernel",
             "bound": "tensor" if algo_used == "tc" else "fp32-fma",
             "achieved": flops_alg / k1_s / 1e12, "peak": peaks["tensor"], "unit": "TFLOP/s",
@@ -304,7 +308,10 @@ def main():
             "peak_source": f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops (burst; fp16 runs at the same rate)",
             "executed_tflops": exec_mult * flops_alg / k1_s / 1e12,
             "executed_frac": exec_mult * flops_alg / k1_s / 1e12 / peaks["tensor"],
-            "executed_note": "3 fp16 products per fp32 product (hi/lo split) and taps padded 401->416",
+            "executed_note": "3 fp16 products per fp32 product (hi/lo split), taps padded 401->416, times the share of "
+                             "(channel, k-step) pairs the support pruning keeps (active channels per k-step below)",
+            "pruning": None if not sched else {"executed_fraction": exec_frac, "active_channels_per_kstep": sched["active"],
+                                               "channels_per_group": sched["channels_per_group"]},
             "k1_ms": ms_k1, "k0_ms": ms_k0, "k2_ms": ms_k2, "launches_profiled": n_prof,
             "k1_sm_cycles": k1_cyc, "k1_sm_mhz_effective": (1e3 * k1_cyc / k1_ns) if k1_ns else None,
             "traffic": None,
@@ -324,10 +331,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": W,
             "ms_per_step": ms_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "algo": algo_used, "n_filters": F, "taps": K, "hop": H,
+            "config": {"workload": WORKLOAD, "algo": algo_name, "n_filters": F, "taps": K, "hop": H,
                        "batch_per_gpu": B, "samples_per_clip": T, "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": f"{N_ROTATE} rotating input batches ({N_ROTATE * B * T * 4 / 1e6:.0f} MB > 126 MB L2)",
-                       "arithmetic": "fp16 hi/lo split operands (3 products), fp32 accumulate; ~2^-21 relative"},
+                       "arithmetic": "fp16 hi/lo split operands (3 products), fp32 accumulate; ~2^-21 relative; "
+                                     "taps beyond 5.5 sigma of a filter skipped per 16-tap step (< 2.7e-7 of its peak)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * T * 4,
                     "d2h_bytes_per_step": world * B * F * n_frames * 4, "ms_per_step": e2e_ms / steps,

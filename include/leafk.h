@@ -180,6 +180,13 @@ int leafk_profile_end(float* ms_k0, float* ms_k1, float* ms_k2);
 int leafk_profile_k1_clock(const leafk_config* cfg, int B, int T, const void* workspace, size_t workspace_bytes,
                            long long* cycles, long long* nanoseconds);
 
+/* Profiling / tests only (synchronous copy): the support-pruning schedule k0 wrote for the LAST forward that used
+ * `workspace` with shapes (B,T).  zones[g*16 + 2*(L-1) + {0,1}] = first / last k-step (of n_ksteps 16-tap steps) on
+ * which channel group g runs at least 16*L of its channels_per_group channels, L = 1..channels_per_group/16; the
+ * tensor work of a k-step is proportional to its active channels. */
+int leafk_profile_tc_schedule(const leafk_config* cfg, int B, int T, const void* workspace, size_t workspace_bytes,
+                              int* n_groups, int* channels_per_group, int* n_ksteps, int* zones, int zones_capacity);
+
 /* Introspection used by tests / bench: kernels launched by this thread since the last reset. */
 long long leafk_launch_count(int reset);
 

@@ -21,7 +21,7 @@ BWD_2PRODUCT = 16
 SYMBOLS = (
     "leafk_version", "leafk_last_error", "leafk_num_frames", "leafk_same_padding",
     "leafk_workspace_bytes", "leafk_forward", "leafk_forward_window", "leafk_backward",
-    "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end", "leafk_profile_k1_clock",
+    "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end", "leafk_profile_k1_clock", "leafk_profile_tc_schedule",
     "leafk_forward_host_async", "leafk_event_create", "leafk_event_destroy", "leafk_event_synchronize",
 )
 
@@ -90,6 +90,9 @@ def lib() -> C.CDLL:
         L.leafk_profile_end.argtypes = [C.POINTER(C.c_float)] * 3
         L.leafk_profile_k1_clock.restype = i
         L.leafk_profile_k1_clock.argtypes = [C.POINTER(Config), i, i, vp, sz, C.POINTER(ll), C.POINTER(ll)]
+        L.leafk_profile_tc_schedule.restype = i
+        L.leafk_profile_tc_schedule.argtypes = [C.POINTER(Config), i, i, vp, sz, C.POINTER(i), C.POINTER(i), C.POINTER(i),
+                                                C.POINTER(i), i]
         L.leafk_forward_host_async.restype = i
         L.leafk_forward_host_async.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, i, vp, vp, vp, sz,
                                                vp, vp, vp, vp, vp]

@@ -504,6 +504,27 @@ int leafk_profile_k1_clock(const leafk_config* cfg, int B, int T, const void* wo
   return LEAFK_OK;
 }
 
+int leafk_profile_tc_schedule(const leafk_config* cfg, int B, int T, const void* workspace, size_t workspace_bytes,
+                              int* n_groups, int* channels_per_group, int* n_ksteps, int* zones, int zones_capacity) {
+  if (!cfg || !workspace || !n_groups || !channels_per_group || !n_ksteps || !zones)
+    return fail(LEAFK_EINVAL, "null pointer argument");
+  const int N = leafk_num_frames(T, cfg->K, cfg->H);
+  Geom g;
+  int rc = make_geom(cfg, B, T, T, 0, T, 0, N, TC_TILE, &g);
+  if (rc) return rc;
+  if (pick_algo(cfg, g) != LEAFK_ALGO_TC) return fail(LEAFK_EINVAL, "the tensor-core kernel does not run for this config");
+  Workspace w;
+  int cg, ng;
+  carve(g, 0, g.n_tiles, &w, &cg, &ng);
+  if (w.total > workspace_bytes) return fail(LEAFK_EWORKSPACE, "workspace %zu bytes < %zu needed", workspace_bytes, w.total);
+  if (zones_capacity < ng * tc::ZONE_INTS) return fail(LEAFK_EINVAL, "zones_capacity %d < %d", zones_capacity, ng * tc::ZONE_INTS);
+  const int* dev = (const int*)((const uint8_t*)workspace + w.off_tcmap) + (size_t)ng * (cg / 2);
+  cudaError_t e = cudaMemcpy(zones, dev, sizeof(int) * (size_t)ng * tc::ZONE_INTS, cudaMemcpyDeviceToHost);   // synchronous: profiling only
+  if (e != cudaSuccess) return fail(LEAFK_ECUDA, "schedule read: %s", cudaGetErrorString(e));
+  *n_groups = ng; *channels_per_group = cg; *n_ksteps = g.Kp / tc::KSTEP;
+  return LEAFK_OK;
+}
+
 long long leafk_launch_count(int reset) {
   const long long v = g_launches;
   if (reset) g_launches = 0;

@@ -282,6 +282,42 @@ def k1_clock_probe(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root
     return int(cyc.value), int(ns.value)
 
 
+
+def tc_schedule(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w):
+    """Run one forward and read back the support-pruning schedule of the tensor-core kernel (profiling / tests).
+    Returns dict(n_groups, channels_per_group, n_ksteps, active=[per group: list of active channels per k-step],
+    executed_fraction = executed / unpruned tensor work)."""
+    L = N.lib()
+    x = _check_input(x)
+    B, _, T = x.shape
+    n = spec.num_frames(T)
+    cfg = spec.config(x.dtype)
+    prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, spec.F, n), dtype=torch.float32, device=x.device)
+        ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        N.check(L.leafk_forward(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(out), None, _ptr(ws), ws_bytes,
+                                _stream_ptr(x.device)), "leafk_forward")
+        torch.cuda.synchronize(x.device)
+        ng, cg, ks = C.c_int(0), C.c_int(0), C.c_int(0)
+        zones = (C.c_int * (64 * 16))()
+        N.check(L.leafk_profile_tc_schedule(C.byref(cfg), B, T, _ptr(ws), ws_bytes, C.byref(ng), C.byref(cg), C.byref(ks),
+                                            zones, 64 * 16), "leafk_profile_tc_schedule")
+    del keep
+    active = []
+    for g in range(ng.value):
+        na = [0] * ks.value
+        for lv in range(cg.value // 16):
+            lo, hi = zones[g * 16 + 2 * lv], zones[g * 16 + 2 * lv + 1]
+            for s in range(lo, hi + 1):
+                na[s] += 16
+        active.append(na)
+    total = sum(sum(a) for a in active)
+    return {"n_groups": ng.value, "channels_per_group": cg.value, "n_ksteps": ks.value, "active": active,
+            "executed_fraction": total / float(ng.value * cg.value * ks.value)}
+
+
 def profile_begin() -> None:
     N.lib().leafk_profile_begin()
 

@@ -299,3 +299,61 @@ def test_benchmark_config_subsample_against_oracle():
     prm = O.params_from_state_dict({k: v.detach().cpu() for k, v in fe.state_dict().items()})
     ref = O.forward_f32(x[idx], prm, 401, 160).numpy()
     assert_close(out[idx].numpy(), ref, "cfg2 subsample vs oracle")
+
+
+def _schedule(fe, x):
+    import leaf_pytorch_b200.functional as LF
+    return LF.tc_schedule(fe.spec, x, *[None if q is None else q.detach() for q in fe._param_tuple()])
+
+
+def test_support_pruning_schedule_default_init():
+    """Default mel initialisation: the narrow (high-frequency) filters are skipped on the outer k-steps, every
+    channel runs on the middle k-steps, the schedule is nested/unimodal, and tc_full runs everything."""
+    import leaf_pytorch_b200 as L
+    x = (torch.randn(2, 1, 4000, generator=torch.Generator().manual_seed(0)).clamp_(-4, 4) / 4).cuda()
+    sch = _schedule(L.Leaf(algo="tc").cuda(), x)
+    assert sch["n_groups"] == 1 and sch["channels_per_group"] == 80 and sch["n_ksteps"] == 26
+    na = sch["active"][0]
+    assert max(na) == 80 and na[12] == 80 and min(na) >= 16 and all(v % 16 == 0 for v in na)
+    peak = na.index(80)
+    assert all(na[i] <= na[i + 1] for i in range(peak)) and all(na[i] >= na[i + 1] for i in range(peak, 25))
+    assert 0.5 < sch["executed_fraction"] < 0.9
+    full = _schedule(L.Leaf(algo="tc_full").cuda(), x)
+    assert full["executed_fraction"] == 1.0
+    # two channel groups (F=80): the width-sorted filters are dealt round-robin, so both groups prune alike
+    s80 = _schedule(L.Leaf(n_filters=80, algo="tc").cuda(), x)
+    assert s80["n_groups"] == 2
+    a0, a1 = s80["active"]
+    assert sum(abs(u - v) for u, v in zip(a0, a1)) <= 16 * 6
+
+
+def test_support_pruning_worst_cases_against_oracle():
+    """Inputs and parameters chosen against the pruning: widths at and beyond both clamps (1.5 .. 150 samples), no
+    pooling bias (nothing hides a relative error of the energies), and (a) a full-scale tone far outside most pass
+    bands, (b) a single impulse (the output frames are the squared filter taps themselves, tails included)."""
+    import leaf_pytorch_b200.functional as LF
+    from oracle import leaf_oracle as O
+    F, K, H, T = 40, 401, 160, 4000
+    rng = np.random.Generator(np.random.PCG64(77))
+    sig = np.concatenate([[0.5, 1.499, 2.0, 3.0, 140.0, 150.3, 400.0], rng.uniform(2.0, 60.0, F - 7)]).astype(np.float32)
+    prm = {"kernel": torch.from_numpy(np.stack([rng.uniform(0.0, 3.14, F).astype(np.float32), sig], 1)),
+           "pool_w": torch.full((F,), 0.4), "pool_b": torch.zeros(F),
+           "alpha": torch.full((F,), 0.96), "delta": torch.full((F,), 2.0), "root": torch.full((F,), 2.0),
+           "ema_w": torch.full((F,), 0.04)}
+    t = torch.arange(T, dtype=torch.float32)
+    tone = torch.sin(2.9 * t).reshape(1, 1, T)
+    imp = torch.zeros(1, 1, T)
+    imp[0, 0, 1777] = 1.0
+    noise = (torch.randn(1, 1, T, generator=torch.Generator().manual_seed(5)).clamp_(-4, 4) / 4) * 1e-3
+    x = torch.cat([tone, imp, tone + noise], 0)
+    ref = O.forward_f32(x, prm, K, H).numpy()
+    p = [prm[k].cuda() for k in ("kernel", "pool_w", "pool_b", "alpha", "delta", "root", "ema_w")]
+    outs = {}
+    for algo in ("tc", "tc_full"):
+        spec = LF.LeafSpec(F=F, K=K, H=H, compression=True, algo=algo)
+        out, _ = LF.forward_raw(spec, x.cuda(), *p)
+        torch.cuda.synchronize()
+        outs[algo] = out.cpu().numpy()
+        assert_close(outs[algo], ref, f"pruning worst case / {algo}")
+    sch = LF.tc_schedule(LF.LeafSpec(F=F, K=K, H=H, compression=True, algo="tc"), x.cuda(), *p)
+    assert sch["executed_fraction"] < 0.95
