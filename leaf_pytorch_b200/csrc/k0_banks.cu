@@ -45,10 +45,11 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
                 float* __restrict__ g32, uint8_t* __restrict__ w16, int tc_cg, int tc_groups, TcPrune pr) {
   extern __shared__ float k0_smem[];
   const int f = blockIdx.x;                 // filter (or a zero-padding channel pair when f >= F)
+  const int k_of_thread = blockIdx.y * blockDim.x + threadIdx.x;   // one tap per thread, gridDim.y chunks of taps
   const size_t grp_bytes = tc::b_group_bytes(tc_cg, Kp);
   const int FG = tc_cg / 2, Fp = FG * tc_groups, ks = Kp / tc::KSTEP;
   float* sm_key = k0_smem;
-  int* sm_pos = reinterpret_cast<int*>(k0_smem + Fp);
+  int* sm_pos = reinterpret_cast<int*>(k0_smem + Fp);       // rank | first active k-step << 8 | last << 16 (ks <= 128)
   int* sm_na = sm_pos + Fp;
   int my_pos = 0;
   if (w16 != nullptr) {
@@ -62,21 +63,25 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
         const float kj = sm_key[j];
         r += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
       }
-      sm_pos[i] = r;
+      int lo, hi;
+      tc::kstep_range(ki, pr.c, K, Kp, &lo, &hi);
+      sm_pos[i] = r | (lo << 16) | (hi << 24);
     }
     __syncthreads();
-    my_pos = sm_pos[f < Fp ? f : 0];
+    my_pos = sm_pos[f < Fp ? f : 0] & 0xffff;
     const int my_grp = tc::group_of(my_pos, tc_groups);
     for (int s = threadIdx.x; s < ks; s += blockDim.x) {
       int cnt = 0;
-      for (int j = 0; j < Fp; ++j)
-        cnt += (tc::group_of(sm_pos[j], tc_groups) == my_grp && tc::kstep_active(sm_key[j], pr.c, s, K)) ? 1 : 0;
+      for (int j = 0; j < Fp; ++j) {
+        const int v = sm_pos[j];
+        cnt += (tc::group_of(v & 0xffff, tc_groups) == my_grp && s >= ((v >> 16) & 0xff) && s <= ((v >> 24) & 0xff)) ? 1 : 0;
+      }
       int nf = (cnt + 7) / 8 * 8;
       if (nf > FG || s == tc::first_kstep(Kp)) nf = FG;
       sm_na[s] = 2 * nf;
     }
     __syncthreads();
-    if (f < Fp) {
+    if (f < Fp && blockIdx.y == 0) {
       if (threadIdx.x == 0) pr.perm[my_grp * FG + tc::slot_of(my_pos, tc_groups)] = f;
       if (tc::slot_of(my_pos, tc_groups) == 0 && threadIdx.x < tc_cg / 16) {     // the group's first filter publishes the zone table
         const int L = threadIdx.x + 1;
@@ -101,7 +106,7 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
     *reinterpret_cast<__half*>(gb + tc::p_hi_corr(tc_cg, Kp, c, na, k)) = hi;
   };
   if (f >= F) {                             // padded channels: zero taps in both layouts
-    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+    for (int k = k_of_thread; k < Kp; k += gridDim.y * blockDim.x) {
       for (int q = 0; q < 2; ++q) {
         const int c = 2 * f + q;
         if (c < C2p) w32[(size_t)k * C2p + c] = 0.f;
@@ -124,7 +129,7 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
   (void)frexpf(norm, &wexp);                // norm = m * 2^wexp, m in [0.5,1)
   const int wshift = 14 - wexp;             // norm * 2^wshift in [2^13, 2^14)
 
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && blockIdx.y == 0) {
     float* c = cprm + (size_t)f * 8;
     c[CP_MU] = mu;
     c[CP_SIGMA] = sg;
@@ -137,7 +142,7 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
     c[CP_PAD] = 0.f;
   }
 
-  for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+  for (int k = k_of_thread; k < Kp; k += gridDim.y * blockDim.x) {
     float wr = 0.f, wi = 0.f;
     if (k < K) {
       const float tau = (float)(k - K / 2);
@@ -287,7 +292,10 @@ void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, i
   const int Fp = tc_cg * tc_groups / 2;
   if (w16 != nullptr && Fp > nblk) nblk = Fp;
   const size_t smem = (w16 != nullptr) ? sizeof(float) * (2 * (size_t)Fp + Kp / tc::KSTEP) : 0;
-  k0_banks_kernel<<<nblk, 128, smem, stream>>>(kernel, pool_w, bc, F, K, Kp, C2p, cprm, w32, g32, w16, tc_cg,
+  // one tap per thread: gridDim.y chunks of 128 taps (the kernel is latency-bound: sincosf + expf + scattered
+  // 2-byte stores per tap; 40 blocks looping over 416 taps took 14 us)
+  const dim3 grid((unsigned)nblk, (unsigned)((Kp + 127) / 128));
+  k0_banks_kernel<<<grid, 128, smem, stream>>>(kernel, pool_w, bc, F, K, Kp, C2p, cprm, w32, g32, w16, tc_cg,
                                                tc_groups, TcPrune{tc_perm, tc_zones, prune_c});
 }
 

@@ -83,13 +83,15 @@ __host__ __device__ inline size_t p_hi_corr(int CG, int Kp, int c, int na, int k
   if (c < CG - na / 2) return 2 * r1_bytes(CG, Kp) + region_offset(h, c - h + na / 2, k);
   return 2 * r1_bytes(CG, Kp) + r2_bytes(CG, Kp) + region_offset(h, c - h, k);
 }
-// inside the support of a filter of width sigma?  (k-step s of a K-tap window, prune factor c; c <= 0: always)
-__host__ __device__ inline bool kstep_active(float sigma, float c, int s, int K) {
-  if (!(c > 0.f)) return true;
-  if (sigma < 0.f) return false;                            // padding filter
-  const int k0 = s * KSTEP, k1 = (k0 + KSTEP - 1 < K - 1) ? k0 + KSTEP - 1 : K - 1, kc = K / 2;
-  const int dmin = (kc < k0) ? k0 - kc : ((kc > k1) ? kc - k1 : 0);
-  return (float)dmin <= ceilf(c * sigma);
+// k-steps [lo, hi] that hold a tap inside the support |tau| <= ceil(c * sigma) of a filter of width sigma
+// (K-tap window, tau = k - K/2).  c <= 0: every k-step; sigma < 0 (padding filter): none (lo > hi).
+__host__ __device__ inline void kstep_range(float sigma, float c, int K, int Kp, int* lo, int* hi) {
+  if (!(c > 0.f)) { *lo = 0; *hi = Kp / KSTEP - 1; return; }
+  if (sigma < 0.f) { *lo = 1; *hi = 0; return; }
+  const float Rf = ceilf(c * sigma);
+  const int R = Rf > (float)K ? K : (int)Rf, kc = K / 2;
+  const int k0 = kc - R < 0 ? 0 : kc - R, k1 = kc + R > K - 1 ? K - 1 : kc + R;
+  *lo = k0 / KSTEP; *hi = k1 / KSTEP;
 }
 constexpr float PRUNE_C = 5.5f;      // default support radius in units of sigma
 // k-step the forward kernel issues first (accumulate = 0): k0 keeps every channel of every group active there

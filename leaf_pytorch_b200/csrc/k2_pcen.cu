@@ -19,49 +19,43 @@ namespace leafk {
 
 constexpr int K2_WARPS = 8;
 
-__device__ __forceinline__ int ceil_div_i(int a, int b) {     // b > 0, a may be negative
-  return (a >= 0) ? (a + b - 1) / b : -((-a) / b);
-}
-
 // x^y for x > 0 as exp2(y*log2 x) with the accurate log2f/exp2f (no fast-math): ~1e-7 * max(1,|y log2 x|)
 // relative, a third of the instructions of powf (whose special-case handling is not needed: x = floor + M > 0;
 // a negative delta gives NaN exactly like powf / the reference).
 __device__ __forceinline__ float pow_pos(float x, float y) { return exp2f(y * log2f(x)); }
 
+// q = a / d for 0 <= a < 2^32 with the round-up magic number m = floor(2^64 / d) + 1 (exact for every 32-bit a);
+// the frame <-> tile arithmetic below needs two divisions by the hop per load, and a hardware-less integer
+// division costs ~25 instructions.
+__device__ __forceinline__ unsigned div_magic(unsigned a, unsigned long long m) {
+  return m == 0ULL ? a : (unsigned)__umul64hi((unsigned long long)a, m);      // m = 0 encodes d = 1
+}
+
 __global__ void __launch_bounds__(K2_WARPS * 32)
-k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, int tl_shift) {
+k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, int tl_shift, unsigned long long hop_magic) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rows = g.B * g.F;
   const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;       // clip length <= 2^30 (checked on the host)
   const int n_end = g.n_begin + g.n_count;
+  const size_t tile_stride = (size_t)g.F * g.SL;
 
   for (int row = blockIdx.x * K2_WARPS + warp; row < rows; row += gridDim.x * K2_WARPS) {
-    const int b = row / g.F, f = row % g.F;
-    float w = 0.f, alpha = 1.f, delta = 0.f, q = 1.f, dq = 0.f;
-    if (a.compression) {
-      w = fminf(fmaxf(__ldg(a.ema_w + f), 0.f), 1.f);          // postprocessing.py:14
-      alpha = fminf(__ldg(a.alpha + f), 1.0f);                 // postprocessing.py:63
-      q = 1.0f / fmaxf(__ldg(a.root + f), 1.0f);               // postprocessing.py:64-65
-      delta = __ldg(a.delta + f);
-      dq = pow_pos(delta, q);
-    }
-    const float om = 1.0f - w;
-    const float bias = a.pool_b ? __ldg(a.pool_b + f) : 0.f;
-    float carry = 0.f;
-    bool have_carry = false;
-    if (a.compression && a.ema_in != nullptr) {
-      carry = a.ema_in[(size_t)b * g.F + f];
-      have_carry = true;
-    }
-    const float* pbase = ppart + (size_t)b * g.n_tiles * g.F * g.SL + (size_t)f * g.SL;
+    const int b = row / g.F, f = row - b * g.F;
+    const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + (size_t)f * g.SL;
     float* orow = a.out + (size_t)b * a.ldo_b + (size_t)f * a.ldo_f;
     float* prow = a.saved_p ? a.saved_p + (size_t)b * a.ldo_b + (size_t)f * a.ldo_f : nullptr;
+
+    float w = 0.f, alpha = 1.f, delta = 0.f, q = 1.f, dq = 0.f, om = 1.f, bias = 0.f;
+    float carry = 0.f;
+    bool have_carry = false;
+    bool have_prm = false;
 
     // 128 frames per step: 4 independent groups of 32 consecutive frames (lane = frame within group), so the
     // loads, the 4 local scans and the 4 PCEN evaluations of a step overlap; only 4 FMAs chain the carry.
     for (int n0 = g.n_begin; n0 < n_end; n0 += 128) {
       float p[4];
       bool ok[4];
+      // partial pooled sums first (the longest latency of the row), parameters while they are in flight
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int n = n0 + 32 * u + lane;
@@ -74,14 +68,33 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
           const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
           float s = 0.f;
           for (int i = i0; i <= i1; ++i) {                    // <= ceil(K/TL)+1 tiles, in tile order
-            const int ts = te_lo + (i << tl_shift);
-            int nf = ceil_div_i(ts + g.padL - g.K + 1, g.H);
+            // first frame whose window reaches the tile start ts: max(n_begin, ceil((ts + padL - K + 1) / H))
+            const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
+            int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
             if (nf < g.n_begin) nf = g.n_begin;
-            s += __ldg(pbase + (size_t)i * g.F * g.SL + (n - nf));
+            s += __ldg(pbase + (size_t)i * tile_stride + (n - nf));
           }
-          p[u] = fmaxf(s + bias, a.clamp_min);                // pooling.py:41, frontend.py:84
+          p[u] = s;
         }
       }
+      if (!have_prm) {
+        have_prm = true;
+        bias = a.pool_b ? __ldg(a.pool_b + f) : 0.f;
+        if (a.compression) {
+          w = fminf(fmaxf(__ldg(a.ema_w + f), 0.f), 1.f);          // postprocessing.py:14
+          alpha = fminf(__ldg(a.alpha + f), 1.0f);                 // postprocessing.py:63
+          q = 1.0f / fmaxf(__ldg(a.root + f), 1.0f);               // postprocessing.py:64-65
+          delta = __ldg(a.delta + f);
+          dq = pow_pos(delta, q);
+          om = 1.0f - w;
+          if (a.ema_in != nullptr) {
+            carry = a.ema_in[(size_t)b * g.F + f];
+            have_carry = true;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = fmaxf(p[u] + bias, a.clamp_min);   // pooling.py:41, frontend.py:84
       float o[4] = {p[0], p[1], p[2], p[3]};
       if (a.compression) {
         if (!have_carry) {                                    // smoother starts at the first frame
@@ -126,10 +139,12 @@ cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cuda
   while ((1 << tl_shift) < g.TL) ++tl_shift;
   if ((1 << tl_shift) != g.TL) return cudaErrorInvalidValue;   // tile lengths are powers of two
   const long long rows = (long long)g.B * g.F;
+  // one warp per row; blocks beyond the resident wave are scheduled as earlier ones retire (rows past 2^31/8
+  // blocks loop inside the kernel)
   long long blocks = (rows + K2_WARPS - 1) / K2_WARPS;
-  const long long cap = 148LL * 8;                             // one resident wave; rows beyond loop
-  if (blocks > cap) blocks = cap;
-  k2_pcen_kernel<<<(unsigned)blocks, K2_WARPS * 32, 0, stream>>>(g, ppart, a, tl_shift);
+  if (blocks > (1LL << 20)) blocks = 1LL << 20;
+  const unsigned long long hop_magic = ~0ULL / (unsigned long long)g.H + 1ULL;
+  k2_pcen_kernel<<<(unsigned)blocks, K2_WARPS * 32, 0, stream>>>(g, ppart, a, tl_shift, hop_magic);
   return cudaGetLastError();
 }
 
