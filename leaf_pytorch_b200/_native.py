@@ -11,7 +11,8 @@ import ctypes as C
 import os
 import threading
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libleafk.so")
+# LEAFK_LIB (development only): load another build of the same library, e.g. a timing-experiment variant
+LIB_PATH = os.environ.get("LEAFK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libleafk.so")
 
 ALGO_AUTO, ALGO_FP32, ALGO_TC = 0, 1, 2
 TC_NOPRUNE = 32        # LEAFK_TC_NOPRUNE: every filter over all taps (no support pruning of the k-steps)

@@ -35,6 +35,13 @@
 #include "tc_ptx.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdio>
+
+#ifndef LEAFK_EXP
+#define LEAFK_EXP 0      // timing experiments only (results wrong): 1 = no epilogue loads + arithmetic, 2 = producers skip the
+                         // copies, 4 = epilogue loads only, 8 = epilogue arithmetic only,
+                         // 16 = no epilogue work on the MMA warp's scheduler (quadrant 0), 32 = only there
+#endif
 
 namespace leafk {
 
@@ -69,7 +76,7 @@ __device__ __forceinline__ void build_copy(tc::Misc* misc, const uint4* sth4, co
                                            int acb, int nchunk, int ptid, int lane, int it) {
   mbar_wait(&misc->a_empty[P], (uint32_t)((it & 1) ^ 1));
   constexpr int s = P >> 1;
-  for (int j = ptid; j < 2 * nchunk; j += tc::PROD_THREADS) {
+  for (int j = ptid; j < ((LEAFK_EXP & 2) ? 0 : 2 * nchunk); j += tc::PROD_THREADS) {
     const int lo = j >= nchunk;
     const int jj = lo ? j - nchunk : j;
     const uint4* src = lo ? stl4 : sth4;
@@ -148,6 +155,50 @@ __device__ __forceinline__ void issue_outer_zones(uint32_t d, uint64_t a_hi, uin
   }
 }
 
+// ---- tile-end reduction over the 32 rows of a warp ----------------------------------------------------------
+// Sum v[f][0..N) over the lanes by recursive halving, NFR independent arrays at once: at exchange distance D the
+// lanes with bit D clear keep the lower half of the indices and receive the partner's partial sums of it, the
+// others the upper half; after the last step lane L holds the complete sums of ONE index,
+// halving_index<N0,16>(L) (-1: a padding slot), for every f.  ~N shuffles per array instead of 5 N, and the NFR
+// arrays advance together, so a tile costs 5 dependent shuffle levels in all.
+template <int NFR, int N, int D>
+__device__ __forceinline__ void halving_multi(const float (&v)[NFR][N], int lane, float (&out)[NFR]) {
+  if constexpr (N == 1) {
+#pragma unroll
+    for (int f = 0; f < NFR; ++f) out[f] = v[f][0];
+#pragma unroll
+    for (int o = D; o > 0; o >>= 1) {
+#pragma unroll
+      for (int f = 0; f < NFR; ++f) out[f] += __shfl_xor_sync(0xffffffffu, out[f], o);
+    }
+  } else {
+    static_assert(D >= 1, "more values than lanes");
+    constexpr int H = (N + 1) / 2;
+    const bool up = (lane & D) != 0;
+    float k[NFR][H];
+#pragma unroll
+    for (int f = 0; f < NFR; ++f) {
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float lo_v = v[f][i], hi_v = (i + H < N) ? v[f][i + H < N ? i + H : 0] : 0.f;
+        k[f][i] = (up ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, up ? lo_v : hi_v, D);
+      }
+    }
+    halving_multi<NFR, H, D / 2>(k, lane, out);
+  }
+}
+template <int N, int D>
+__device__ __forceinline__ int halving_index(int lane) {
+  if constexpr (N == 1 || D == 0) {
+    return 0;
+  } else {
+    constexpr int H = (N + 1) / 2;
+    const int inner = halving_index<H, D / 2>(lane);
+    const int idx = ((lane & D) ? H : 0) + inner;
+    return (inner < 0 || idx >= N) ? -1 : idx;
+  }
+}
+
 // KS > 0: number of k-steps known at compile time (26 for the default 401-tap window): the MMA issue loop is
 // fully unrolled with immediate descriptor offsets -- with a runtime trip count the per-iteration descriptor
 // arithmetic made the single issuing lane the bottleneck (149 cycles per k-step measured vs 124 issued tight).
@@ -164,13 +215,15 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   constexpr uint32_t IDESC_CORR = idesc_f16(256, CG);
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  const SmemPlan sp = smem_plan(CG, g.Kp, g.SL, MODE);
+  const SmemPlan sp = smem_plan(CG, g.Kp, g.SL, MODE, NSLOT);
   uint8_t* s_w = smem + sp.off_w;
   uint8_t* s_acopy = smem + sp.off_acopy;
   float* s_st32 = reinterpret_cast<float*>(smem + sp.off_st32);
   __half* s_sth = reinterpret_cast<__half*>(smem + sp.off_sth);
   __half* s_stl = reinterpret_cast<__half*>(smem + sp.off_stl);
   float* s_pw = reinterpret_cast<float*>(smem + sp.off_pw);
+  float* s_red = reinterpret_cast<float*>(smem + sp.off_red);
+  int4* s_out = reinterpret_cast<int4*>(smem + sp.off_out);
   Misc* misc = reinterpret_cast<Misc*>(smem + sp.off_misc);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -287,6 +340,9 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       const uint64_t b1_step = (uint64_t)((CG * 32) >> 4), b2_step = (uint64_t)(((CG / 2) * 32) >> 4);
       // Forward: zone bounds of this channel group (k0's support pruning), made warp-uniform with a redux so
       // that the zone loops run on uniform registers.
+#if (LEAFK_EXP & 64)
+      long long dbg_t[3] = {0, 0, 0};
+#endif
       constexpr int LMAX = CG / 16;
       int zlo[LMAX], zhi[LMAX];
       if constexpr (MODE == 0) {
@@ -303,8 +359,18 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         for (int p = 0; p < NPHASE; ++p) {
           const int gp = it * NPHASE + p;
           const int st = gp % NST;
+#if (LEAFK_EXP & 64)
+          const long long tq0 = clock64();
+#endif
           mbar_wait_cluster(&misc->a_full[p], (uint32_t)(it & 1));
+#if (LEAFK_EXP & 64)
+          const long long tq1 = clock64();
+#endif
           mbar_wait_cluster(&misc->acc_empty[st], (uint32_t)(((gp / NST) & 1) ^ 1));
+#if (LEAFK_EXP & 64)
+          const long long tq2 = clock64();
+          dbg_t[0] += tq1 - tq0; dbg_t[1] += tq2 - tq1;
+#endif
           tc_fence_after();
           const uint32_t d = tmem + (uint32_t)(st * NB);
           const uint64_t a_hi = smem_desc(a_base + (uint32_t)((2 * p) * sp.acb), 16, 128);
@@ -339,8 +405,15 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
             mma_commit_pair(&misc->acc_full[st]);
           }
           __syncwarp();
+#if (LEAFK_EXP & 64)
+          dbg_t[2] += clock64() - tq2;
+#endif
         }
       }
+#if (LEAFK_EXP & 64)
+      if (blockIdx.x == 0 && lane == 0)
+        printf("MMA warp: wait a_full %lld, wait acc_empty %lld, issue %lld cycles (tiles %d)\n", dbg_t[0], dbg_t[1], dbg_t[2], it);
+#endif
     }
   } else if constexpr (MODE == 0) {
     // =========================================== EPILOGUE (forward) =============================
@@ -349,6 +422,9 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
     const int m = 32 * q + lane;                        // accumulator row
     // this thread's filters: sorted positions hh*FPT + i of the group; perm gives the filter they belong to
     const int* gperm = tm.perm + (size_t)grp * (CG / 2);
+#if (LEAFK_EXP & 64)
+    long long dbg_e[5] = {0, 0, 0, 0, 0};
+#endif
     float pa[FPT];
 #pragma unroll
     for (int i = 0; i < FPT; ++i) {
@@ -357,6 +433,16 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
     }
     const float centre = 0.5f * (float)(g.K - 1);
     const int n_last = g.n_begin + g.n_count - 1;
+    float* red = s_red + (size_t)e * FPT * 33;          // this warp's transpose buffer (generic tile-end row sums)
+    const int red_fi = halving_index<FPT, 16>(lane);    // filter whose row sum the halving reduction leaves in this lane
+    // output table of the tile-end store (slot fastest, the layout K2 reads); read back by the same threads only
+    for (int idx = etid; idx < g.SL * (CG / 2); idx += EPI_WARPS * 32) {
+      const int fl = idx / g.SL, slot = idx - fl * g.SL;
+      const int f = __ldg(gperm + fl);                      // sorted position -> filter
+      int4 o = make_int4(((fl / FPT) * 4 * g.SL + slot) * FPT + fl % FPT, -1, 0, 0);
+      if (f < g.F) { o.y = f * g.SL + slot; o.z = (int)__ldg(cprm + (size_t)f * 8 + CP_WSCALE); }
+      s_out[idx] = o;
+    }
     int it = 0;
     for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
       const long long u = 2 * pu + rank;
@@ -387,16 +473,32 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
           const float kc = (float)k - centre;
           dj[j] = ok ? kc * kc : 1.0e30f;               // ex2(pa * 1e30) = 0: outside the window
         }
+#if (LEAFK_EXP & 64)
+        const long long te0 = clock64();
+#endif
         mbar_wait(&misc->acc_full[st], (uint32_t)((gp / NST) & 1));
+#if (LEAFK_EXP & 64)
+        const long long te1 = clock64();
+        dbg_e[0] += te1 - te0;
+#endif
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + hh * (CG / 2));
         const uint32_t tlo = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + 2 * CG - 8 - hh * (CG / 2));
 #pragma unroll
-        for (int c = 0; c < FPT / 4; ++c) {
+        for (int c = 0; c < (((LEAFK_EXP & 1) || ((LEAFK_EXP & 16) && q == 0) || ((LEAFK_EXP & 32) && q != 0)) ? 0 : FPT / 4); ++c) {
           // hi products of the 4 filters at columns hh*CG/2 + 8c ..; their lo products sit in the mirrored
           // 8-column block of the lo half, filters in reverse order (k1_tc_layout.cuh)
           float ym[8], yc[8];
-          tmem_ld8x2_sync(taddr + 8 * c, tlo - 8 * c, ym, yc);
+          if constexpr ((LEAFK_EXP & 8) != 0) {            // experiment: the arithmetic without the TMEM loads
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ym[i] = dj[0] * (float)(i + c); yc[i] = dj[1] + (float)i; }
+          } else {
+            tmem_ld8x2_sync(taddr + 8 * c, tlo - 8 * c, ym, yc);
+          }
+          if constexpr ((LEAFK_EXP & 4) != 0) {            // experiment: the TMEM loads without the arithmetic
+            acc[0][0] += ym[0] + yc[7];
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float re = ym[2 * i] + yc[2 * (3 - i)], im = ym[2 * i + 1] + yc[2 * (3 - i) + 1];
@@ -409,47 +511,106 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_rank0(&misc->acc_empty[st]);
+#if (LEAFK_EXP & 64)
+        dbg_e[1] += clock64() - te1;
+#endif
       }
+#if (LEAFK_EXP & 64)
+      const long long te2 = clock64();
+#endif
 
       // ---- reduce over the rows of this warp: per-frame sums -> s_pw[buf][e][slot][fi] ----------
+      // This section is on the critical path: while the epilogue warps are in it nobody drains the accumulator
+      // stages, and the three stages cover only ~8 k cycles of MMAs.  The shared-memory pipe is ~86 % busy with
+      // tensor-core operand fetches, so every dependent trip through it (shuffle level, store/load pair) costs
+      // 150-350 cycles: the row sums therefore run as ONE recursive-halving reduction over all (<= 5) frames at once
+      // -- 5 dependent shuffle levels per tile instead of 5 per frame or per (frame, filter).
       float* pw_buf = s_pw + (size_t)(it & 1) * (EPI_WARPS * g.SL * FPT);
       float* pw = pw_buf + (size_t)e * g.SL * FPT;
       for (int i = lane; i < g.SL * FPT; i += 32) pw[i] = 0.f;
       __syncwarp();
       const int nb_lo = __shfl_sync(0xffffffffu, nb, 0);
       int nb_hi = __shfl_sync(0xffffffffu, nb, 31) + NSLOT - 1;
-      if (nb_hi > n_last) nb_hi = n_last;
-      for (int n = nb_lo; n <= nb_hi; ++n) {
-        const int slot = n - n_first;
-        if (slot >= g.SL) break;
-        const int j = n - nb;
+      constexpr int NFR = NSLOT + 2;                        // frames the fast path covers
+      if (NSLOT == 3 && nb_hi - nb_lo < NFR) {
+        if (nb_hi > n_last) nb_hi = n_last;
+        const int eo = nb - nb_lo;                          // 0..2: this lane's first frame relative to the warp's
+        constexpr int H1 = (FPT + 1) / 2;
+        const bool up = (lane & 16) != 0;
+        float k1[NFR][H1];
 #pragma unroll
-        for (int i = 0; i < FPT; ++i) {
-          float v = 0.f;
+        for (int d = 0; d < NFR; ++d) {
 #pragma unroll
-          for (int jj = 0; jj < NSLOT; ++jj) v = (j == jj) ? acc[i][jj] : v;
+          for (int i = 0; i < H1; ++i) {
+            float lo_v = 0.f, hi_v = 0.f;
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0) pw[slot * FPT + i] = v;
+            for (int jj = 0; jj < NSLOT; ++jj) {
+              if (d - jj >= 0 && d - jj <= 2) {             // frame d is slot jj of the lanes with eo == d - jj
+                lo_v = (eo == d - jj) ? acc[i][jj] : lo_v;
+                if (i + H1 < FPT) hi_v = (eo == d - jj) ? acc[i + H1 < FPT ? i + H1 : 0][jj] : hi_v;
+              }
+            }
+            k1[d][i] = (up ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, up ? lo_v : hi_v, 16);
+          }
+        }
+        float tot[NFR];
+        halving_multi<NFR, H1, 8>(k1, lane, tot);
+#pragma unroll
+        for (int d = 0; d < NFR; ++d) {
+          const int slot = nb_lo + d - n_first;
+          if (red_fi >= 0 && nb_lo + d <= nb_hi && slot < g.SL) pw[slot * FPT + red_fi] = tot[d];
+        }
+      } else {
+        // generic geometry (more frames per warp): row sums through the transpose buffer, one frame at a time
+        if (nb_hi > n_last) nb_hi = n_last;
+        for (int n = nb_lo; n <= nb_hi; ++n) {
+          const int slot = n - n_first;
+          if (slot >= g.SL) break;
+          const int j = n - nb;
+#pragma unroll
+          for (int i = 0; i < FPT; ++i) {
+            float v = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < NSLOT; ++jj) v = (j == jj) ? acc[i][jj] : v;
+            red[i * 33 + lane] = v;
+          }
+          __syncwarp();
+          if (lane < FPT) {
+            const float* rr = red + lane * 33;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; r += 4) { s0 += rr[r]; s1 += rr[r + 1]; s2 += rr[r + 2]; s3 += rr[r + 3]; }
+            pw[slot * FPT + lane] = (s0 + s1) + (s2 + s3);
+          }
+          __syncwarp();
         }
       }
+#if (LEAFK_EXP & 64)
+      const long long te3 = clock64();
+      dbg_e[3] += te3 - te2;
+#endif
       named_bar_sync(BAR_EPI, EPI_WARPS * 32);
       // ---- fixed-order sum over the four row quadrants, undo the scaling, store -----------------
       const int sx = misc->sx_ring[it & 3];
       float* dst = ppart + ((size_t)b * g.n_tiles + tile) * g.SL * g.F;
       for (int idx = etid; idx < g.SL * (CG / 2); idx += EPI_WARPS * 32) {
-        const int fl = idx / g.SL, slot = idx % g.SL;       // (filter, slot) layout, slot fastest
-        const int h2 = fl / FPT, fi = fl % FPT;
-        const int f = __ldg(gperm + fl);                    // sorted position -> filter
-        if (valid && f < g.F) {
+        const int4 o = s_out[idx];
+        if (valid && o.y >= 0) {
+          const float* src = pw_buf + o.x;
           float s = 0.f;
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) s += pw_buf[((size_t)(h2 * 4 + qq) * g.SL + slot) * FPT + fi];
-          const int wsh = (int)__ldg(cprm + (size_t)f * 8 + CP_WSCALE);
-          dst[(size_t)f * g.SL + slot] = scalbnf(s, -2 * (sx + wsh));
+          for (int qq = 0; qq < 4; ++qq) s += src[(size_t)qq * g.SL * FPT];
+          dst[o.y] = scalbnf(s, -2 * (sx + o.z));
         }
       }
+#if (LEAFK_EXP & 64)
+      dbg_e[2] += clock64() - te2;
+#endif
     }
+#if (LEAFK_EXP & 64)
+    if (blockIdx.x == 0 && tid == 0)
+      printf("epilogue warp 0: wait acc_full %lld, phase work %lld, tile end %lld (reduction %lld) cycles\n", dbg_e[0], dbg_e[1], dbg_e[2], dbg_e[3]);
+#endif
   } else {
     // =========================================== EPILOGUE (backward) ============================
     constexpr int FB = CG / 6;                          // filters per group
@@ -678,7 +839,7 @@ cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, cons
   if (err != cudaSuccess) return err;
   const int grid = tc::pair_grid(n_sm, tc_groups, (long long)g.B * g.n_tiles);
   const int nslot = tc::slots_per_thread(g.K, g.H);
-  const int smem = tc::smem_plan(tc_cg, g.Kp, g.SL).total;
+  const int smem = tc::smem_plan(tc_cg, g.Kp, g.SL, 0, nslot > 3 ? 5 : 3).total;
   switch (tc_cg) {
     case 16: return launch_cg<16>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
     case 32: return launch_cg<32>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);

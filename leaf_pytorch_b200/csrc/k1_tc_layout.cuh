@@ -108,11 +108,11 @@ struct SmemPlan {
   int CL;          // halves per shifted copy: 8*127 + Kp
   int LX;          // samples staged per tile: CL + 8
   int acb;         // bytes per copy
-  int off_w, off_acopy, off_st32, off_sth, off_stl, off_pw, off_prog, off_misc, total;
+  int off_w, off_acopy, off_st32, off_sth, off_stl, off_pw, off_red, off_out, off_misc, total;
 };
 
 // mode 0: forward (pooling partial buffers), mode 1: backward (small reduction scratch instead)
-__host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode = 0) {
+__host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode = 0, int nslot = 3) {
   SmemPlan s;
   s.CL = 8 * 127 + Kp;
   s.LX = s.CL + 8;
@@ -124,8 +124,14 @@ __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode =
   s.off_sth = off;    off += (s.LX * 2 + 15) / 16 * 16;
   s.off_stl = off;    off += (s.LX * 2 + 15) / 16 * 16;
   s.off_pw = off;     off += (mode == 0) ? 2 * 8 * SL * (CG / 4) * 4 : 8 * 32 * 4;
-  s.off_prog = (off + 15) / 16 * 16;
-  s.off_misc = s.off_prog;
+  // forward: per epilogue warp a (CG/4 filters) x 33 float transpose buffer (generic tile-end row sums)
+  s.off_red = (off + 15) / 16 * 16;
+  // forward: per (filter, slot) output of a tile {offset in the reduction buffer, offset in the tile's partial-sum
+  // block or -1, bank scale of the filter, 0}: tile independent, built once per CTA
+  s.off_out = s.off_red + ((mode == 0) ? 8 * (CG / 4) * 33 * 4 : 0);
+  s.off_out = (s.off_out + 15) / 16 * 16;
+  s.off_misc = s.off_out + ((mode == 0) ? SL * (CG / 2) * 16 : 0);
+  s.off_misc = (s.off_misc + 15) / 16 * 16;
   s.total = s.off_misc + 512;
   return s;
 }
@@ -151,7 +157,7 @@ __host__ __device__ inline bool channel_groups(int C2, int Kp, int SL, int nslot
     int cg = (C2 + g - 1) / g;
     cg = (cg + 15) / 16 * 16;
     if (cg > max_cg) continue;
-    if (smem_plan(cg, Kp, SL).total > SMEM_LIMIT) continue;
+    if (smem_plan(cg, Kp, SL, 0, nslot > 3 ? 5 : 3).total > SMEM_LIMIT) continue;
     *n_groups = (C2 + cg - 1) / cg;
     *CG = cg;
     return true;

@@ -24,13 +24,6 @@ constexpr int K2_WARPS = 8;
 // a negative delta gives NaN exactly like powf / the reference).
 __device__ __forceinline__ float pow_pos(float x, float y) { return exp2f(y * log2f(x)); }
 
-// q = a / d for 0 <= a < 2^32 with the round-up magic number m = floor(2^64 / d) + 1 (exact for every 32-bit a);
-// the frame <-> tile arithmetic below needs two divisions by the hop per load, and a hardware-less integer
-// division costs ~25 instructions.
-__device__ __forceinline__ unsigned div_magic(unsigned a, unsigned long long m) {
-  return m == 0ULL ? a : (unsigned)__umul64hi((unsigned long long)a, m);      // m = 0 encodes d = 1
-}
-
 __global__ void __launch_bounds__(K2_WARPS * 32)
 k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, int tl_shift, unsigned long long hop_magic) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,7 +136,7 @@ cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cuda
   // blocks loop inside the kernel)
   long long blocks = (rows + K2_WARPS - 1) / K2_WARPS;
   if (blocks > (1LL << 20)) blocks = 1LL << 20;
-  const unsigned long long hop_magic = ~0ULL / (unsigned long long)g.H + 1ULL;
+  const unsigned long long hop_magic = div_magic_of((unsigned)g.H);
   k2_pcen_kernel<<<(unsigned)blocks, K2_WARPS * 32, 0, stream>>>(g, ppart, a, tl_shift, hop_magic);
   return cudaGetLastError();
 }

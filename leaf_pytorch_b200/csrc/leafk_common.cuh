@@ -59,6 +59,15 @@ __host__ __device__ inline int last_frame_of(const Geom& g, long long tl) {
   return (int)(n > hi ? hi : n);
 }
 
+// q = a / d for 0 <= a < 2^32 with the round-up magic number m = floor(2^64 / d) + 1 (exact for every 32-bit a;
+// m = 0 encodes d = 1).  A hardware-less integer division by a runtime value costs ~25 instructions.
+__host__ __device__ inline unsigned long long div_magic_of(unsigned d) { return d <= 1u ? 0ULL : ~0ULL / (unsigned long long)d + 1ULL; }
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned div_magic(unsigned a, unsigned long long m) {
+  return m == 0ULL ? a : (unsigned)__umul64hi((unsigned long long)a, m);
+}
+#endif
+
 // ---- workspace layout (all offsets in bytes, 256-aligned) -------------------------------------
 struct Workspace {
   size_t off_cprm;   // float[F*8]   constrained parameters + derived per-filter constants
