@@ -131,7 +131,7 @@ def cpu_port_throughput(B_sample: int, T: int, runs: int = 3):
     return (B_sample * T / SR) / t, t, torch.get_num_threads()
 
 
-def run_reference(args, rank: int, world: int):
+def run_reference(args, rank: int, world: int, emit):
     """--impl reference: the reference's CPU implementation of the path (oracle port; kind 'port')."""
     if rank != 0:
         return
@@ -163,7 +163,7 @@ def run_reference(args, rank: int, world: int):
             "config": {"workload": WORKLOAD, "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -180,8 +180,17 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version banner, ...)
+    # goes to stderr instead
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return
 
     import torch.distributed as dist
@@ -192,6 +201,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from leaf_pytorch_b200.distributed import bind_to_gpu_numa_node
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None     # before any pinned allocation
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -354,7 +365,7 @@ def main():
             v, t, cores = cpu_port_throughput(32, T)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"32 of the {B} clips (1 warm-up + 3 runs, median {t:.2f} s)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -9,10 +9,49 @@ Works with any torch.distributed backend (NCCL on the B200s, gloo in the CPU tes
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it allocates
+    afterwards (first touch) and the threads that fill them are local to the GPU's PCIe root: with one process
+    per GPU the host-to-device copies of the eight ranks otherwise cross the socket interconnect.  Linux only;
+    returns the node, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
 
 
 def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
