@@ -69,27 +69,36 @@ static_assert(sizeof(Misc) <= 512, "Misc must fit the reserved tail");
 }  // namespace tc
 
 
-// Producer step for phase P: wait until the MMAs of phase P of the previous tile have drained, then
-// write copy_P (hi and lo): chunk jj of the copy = staging halves [8jj+P, 8jj+P+8).
-template <int P>
-__device__ __forceinline__ void build_copy(tc::Misc* misc, const uint4* sth4, const uint4* stl4, uint8_t* s_acopy,
-                                           int acb, int nchunk, int ptid, int lane, int it) {
+// Producer step for phase P: wait until the MMAs of phase P of the previous tile have drained, then write copy_P (hi
+// and lo): chunk jj of the copy = staged halves [8jj+P, 8jj+P+8).
+// Each producer thread owns the chunks jj = ptid + c * PROD_THREADS (c < NC) of every
+// copy and keeps the 16 scaled hi / lo halves [8 jj, 8 jj + 16) they are cut from in registers (wh / wl, 8 words per
+// chunk), so a tile costs the shared-memory pipe only the 16 copy stores: the staging round trips (fp32 store + load,
+// half store, two 16-byte loads per 16-byte chunk) were ~850 of the ~1200 wavefronts the producers added per tile to
+// a pipe that the tensor-core operand fetches keep ~90 % busy.
+template <int P, int NC>              // NC = chunks per thread: ceil((127 + Kp/8) / 96), 2 for the 401-tap window, <= 4
+__device__ __forceinline__ void build_copy_regs(tc::Misc* misc, const uint32_t (&wh)[NC][8],
+                                                const uint32_t (&wl)[NC][8], uint8_t* s_acopy, int acb, int nchunk,
+                                                int ptid, int lane, int it) {
   mbar_wait(&misc->a_empty[P], (uint32_t)((it & 1) ^ 1));
   constexpr int s = P >> 1;
-  for (int j = ptid; j < ((LEAFK_EXP & 2) ? 0 : 2 * nchunk); j += tc::PROD_THREADS) {
-    const int lo = j >= nchunk;
-    const int jj = lo ? j - nchunk : j;
-    const uint4* src = lo ? stl4 : sth4;
-    const uint4 c0 = src[jj], c1 = src[jj + 1];
-    const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-    uint4 o;
-    if ((P & 1) == 0) {
-      o = make_uint4(w[s], w[s + 1], w[s + 2], w[s + 3]);
-    } else {
-      o = make_uint4(__funnelshift_r(w[s], w[s + 1], 16), __funnelshift_r(w[s + 1], w[s + 2], 16),
-                     __funnelshift_r(w[s + 2], w[s + 3], 16), __funnelshift_r(w[s + 3], w[s + 4], 16));
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int jj = ptid + c * tc::PROD_THREADS;
+    if (jj < (((LEAFK_EXP & 2) != 0) ? 0 : nchunk)) {
+      uint4 oh, ol;
+      if ((P & 1) == 0) {
+        oh = make_uint4(wh[c][s], wh[c][s + 1], wh[c][s + 2], wh[c][s + 3]);
+        ol = make_uint4(wl[c][s], wl[c][s + 1], wl[c][s + 2], wl[c][s + 3]);
+      } else {
+        oh = make_uint4(__funnelshift_r(wh[c][s], wh[c][s + 1], 16), __funnelshift_r(wh[c][s + 1], wh[c][s + 2], 16),
+                        __funnelshift_r(wh[c][s + 2], wh[c][s + 3], 16), __funnelshift_r(wh[c][s + 3], wh[c][s + 4], 16));
+        ol = make_uint4(__funnelshift_r(wl[c][s], wl[c][s + 1], 16), __funnelshift_r(wl[c][s + 1], wl[c][s + 2], 16),
+                        __funnelshift_r(wl[c][s + 2], wl[c][s + 3], 16), __funnelshift_r(wl[c][s + 3], wl[c][s + 4], 16));
+      }
+      *reinterpret_cast<uint4*>(s_acopy + (size_t)(2 * P) * acb + (size_t)jj * 16) = oh;
+      *reinterpret_cast<uint4*>(s_acopy + (size_t)(2 * P + 1) * acb + (size_t)jj * 16) = ol;
     }
-    *reinterpret_cast<uint4*>(s_acopy + (size_t)(2 * P + lo) * acb + (size_t)jj * 16) = o;
   }
   fence_proxy_async_smem();
   __syncwarp();
@@ -199,6 +208,88 @@ __device__ __forceinline__ int halving_index(int lane) {
   }
 }
 
+// Producer warps (3 warps of each CTA): per tile load the sample window, find its max, scale by a power of two,
+// split to fp16 hi/lo in registers and write the 8 shifted copies, copy p as soon as phase p of the previous tile has
+// been consumed.
+template <int NC>
+__device__ __forceinline__ void producer_loop(const Geom& g, const float* __restrict__ x, const TcReady& rdy,
+                                              const tc::SmemPlan& sp, tc::Misc* misc, uint8_t* s_acopy, int tid, int lane,
+                                              int warp, uint32_t rank, int pair_in_grp, int pairs_in_grp,
+                                              long long n_units, long long n_pair_units) {
+  using namespace tc;
+  const int ptid = tid - PROD_WARP0 * 32;
+  const int nchunk = sp.CL / 8;            // 16-byte chunks per copy
+  int it = 0;
+  for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
+    const long long u = 2 * pu + rank;
+    const bool valid = u < n_units;                // odd unit count: the last pair's rank 1 runs on zeros
+    const int b = valid ? (int)(u / g.n_tiles) : 0, tile = valid ? (int)(u % g.n_tiles) : 0;
+    const long long ts = g.te_lo + (long long)tile * TILE;
+    const size_t xrow = (size_t)b * g.ldx;
+    if (valid && rdy.ready != nullptr && ptid == 0) {       // clip b still in flight over PCIe?
+      const int* flag = rdy.ready + b / rdy.clips_per_flag;
+      int v;
+      unsigned spins = 0;
+      do {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == 0) { __nanosleep(200); if (++spins > (1u << 24)) __trap(); }
+      } while (v == 0);
+    }
+    named_bar_sync(BAR_PROD, PROD_THREADS);        // clip b resident; max scratch of the previous tile consumed
+    // this thread's samples: 16 per chunk (staged index 8 jj .. 8 jj + 15, sample ts - padL + index)
+    float v[NC][16];
+    float mx = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int jj = ptid + c * PROD_THREADS;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int idx = 8 * jj + i;
+        const long long a = ts - g.padL + idx, wi = a - g.t_off;
+        float val = 0.f;
+        if (valid && jj < nchunk && idx < sp.LX && a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win)
+          val = load_sample(x, xrow, wi, g.x_fmt);   // coherent load: may have just landed
+        v[c][i] = val;
+        mx = fmaxf(mx, fabsf(val));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) misc->red[warp - PROD_WARP0] = mx;
+    named_bar_sync(BAR_PROD, PROD_THREADS);
+    mx = fmaxf(misc->red[0], fmaxf(misc->red[1], misc->red[2]));
+    int sx = 0;
+    if (mx > 0.f && mx < 3.0e38f) {
+      int ex;
+      (void)frexpf(mx, &ex);                       // mx = m * 2^ex, m in [0.5,1)
+      sx = 14 - ex;                                // mx * 2^sx in [2^13, 2^14)
+      sx = sx < -100 ? -100 : (sx > 100 ? 100 : sx);
+    }
+    if (ptid == 0) misc->sx_ring[it & 3] = sx;
+    const float scale = ldexpf(1.0f, sx);
+    uint32_t wh[NC][8], wl[NC][8];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a0 = v[c][2 * i] * scale, a1 = v[c][2 * i + 1] * scale;
+        const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+        const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+        wh[c][i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        wl[c][i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+    }
+    build_copy_regs<0, NC>(misc, wh, wl, s_acopy, sp.acb, nchunk, ptid, lane, it);
+    build_copy_regs<1, NC>(misc, wh, wl, s_acopy, sp.acb, nchunk, ptid, lane, it);
+    build_copy_regs<2, NC>(misc, wh, wl, s_acopy, sp.acb, nchunk, ptid, lane, it);
+    build_copy_regs<3, NC>(misc, wh, wl, s_acopy, sp.acb, nchunk, ptid, lane, it);
+    build_copy_regs<4, NC>(misc, wh, wl, s_acopy, sp.acb, nchunk, ptid, lane, it);
+    build_copy_regs<5, NC>(misc, wh, wl, s_acopy, sp.acb, nchunk, ptid, lane, it);
+    build_copy_regs<6, NC>(misc, wh, wl, s_acopy, sp.acb, nchunk, ptid, lane, it);
+    build_copy_regs<7, NC>(misc, wh, wl, s_acopy, sp.acb, nchunk, ptid, lane, it);
+  }
+}
+
 // KS > 0: number of k-steps known at compile time (26 for the default 401-tap window): the MMA issue loop is
 // fully unrolled with immediate descriptor offsets -- with a runtime trip count the per-iteration descriptor
 // arithmetic made the single issuing lane the bottleneck (149 cycles per k-step measured vs 124 issued tight).
@@ -218,9 +309,6 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   const SmemPlan sp = smem_plan(CG, g.Kp, g.SL, MODE, NSLOT);
   uint8_t* s_w = smem + sp.off_w;
   uint8_t* s_acopy = smem + sp.off_acopy;
-  float* s_st32 = reinterpret_cast<float*>(smem + sp.off_st32);
-  __half* s_sth = reinterpret_cast<__half*>(smem + sp.off_sth);
-  __half* s_stl = reinterpret_cast<__half*>(smem + sp.off_stl);
   float* s_pw = reinterpret_cast<float*>(smem + sp.off_pw);
   float* s_red = reinterpret_cast<float*>(smem + sp.off_red);
   int4* s_out = reinterpret_cast<int4*>(smem + sp.off_out);
@@ -271,65 +359,13 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
 
   if (warp >= PROD_WARP0) {
     // =========================================== PRODUCERS ======================================
-    const int ptid = tid - PROD_WARP0 * 32;
-    const int nchunk = sp.CL / 8;            // 16-byte chunks per copy
-    int it = 0;
-    for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
-      const long long u = 2 * pu + rank;
-      const bool valid = u < n_units;                // odd unit count: the last pair's rank 1 runs on zeros
-      const int b = valid ? (int)(u / g.n_tiles) : 0, tile = valid ? (int)(u % g.n_tiles) : 0;
-      const long long ts = g.te_lo + (long long)tile * TILE;
-      const size_t xrow = (size_t)b * g.ldx;
-      if (valid && rdy.ready != nullptr && ptid == 0) {       // clip b still in flight over PCIe?
-        const int* flag = rdy.ready + b / rdy.clips_per_flag;
-        int v;
-        unsigned spins = 0;
-        do {
-          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-          if (v == 0) { __nanosleep(200); if (++spins > (1u << 24)) __trap(); }
-        } while (v == 0);
-      }
-      named_bar_sync(BAR_PROD, PROD_THREADS);        // staging of the previous tile fully consumed; clip b resident
-      float mx = 0.f;
-      for (int i = ptid; i < sp.LX; i += PROD_THREADS) {
-        const long long a = ts - g.padL + i, wi = a - g.t_off;
-        float v = 0.f;
-        if (valid && a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win) v = load_sample(x, xrow, wi, g.x_fmt);   // coherent load: may have just landed
-        s_st32[i] = v;
-        mx = fmaxf(mx, fabsf(v));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (lane == 0) misc->red[warp - PROD_WARP0] = mx;
-      named_bar_sync(BAR_PROD, PROD_THREADS);
-      mx = fmaxf(misc->red[0], fmaxf(misc->red[1], misc->red[2]));
-      int sx = 0;
-      if (mx > 0.f && mx < 3.0e38f) {
-        int ex;
-        (void)frexpf(mx, &ex);                       // mx = m * 2^ex, m in [0.5,1)
-        sx = 14 - ex;                                // mx * 2^sx in [2^13, 2^14)
-        sx = sx < -100 ? -100 : (sx > 100 ? 100 : sx);
-      }
-      if (ptid == 0) misc->sx_ring[it & 3] = sx;
-      const float scale = ldexpf(1.0f, sx);
-      for (int i = ptid; i < sp.LX; i += PROD_THREADS) {
-        const float v = s_st32[i] * scale;
-        const __half h = __float2half_rn(v);
-        s_sth[i] = h;
-        s_stl[i] = __float2half_rn(v - __half2float(h));
-      }
-      named_bar_sync(BAR_PROD, PROD_THREADS);
-      const uint4* sth4 = reinterpret_cast<const uint4*>(s_sth);
-      const uint4* stl4 = reinterpret_cast<const uint4*>(s_stl);
-      build_copy<0>(misc, sth4, stl4, s_acopy, sp.acb, nchunk, ptid, lane, it);
-      build_copy<1>(misc, sth4, stl4, s_acopy, sp.acb, nchunk, ptid, lane, it);
-      build_copy<2>(misc, sth4, stl4, s_acopy, sp.acb, nchunk, ptid, lane, it);
-      build_copy<3>(misc, sth4, stl4, s_acopy, sp.acb, nchunk, ptid, lane, it);
-      build_copy<4>(misc, sth4, stl4, s_acopy, sp.acb, nchunk, ptid, lane, it);
-      build_copy<5>(misc, sth4, stl4, s_acopy, sp.acb, nchunk, ptid, lane, it);
-      build_copy<6>(misc, sth4, stl4, s_acopy, sp.acb, nchunk, ptid, lane, it);
-      build_copy<7>(misc, sth4, stl4, s_acopy, sp.acb, nchunk, ptid, lane, it);
-    }
+    const int cpt = (sp.CL / 8 + PROD_THREADS - 1) / PROD_THREADS;     // 16-byte chunks of a copy per producer thread
+    if (cpt <= 2)
+      producer_loop<2>(g, x, rdy, sp, misc, s_acopy, tid, lane, warp, rank, pair_in_grp, pairs_in_grp, n_units, n_pair_units);
+    else if (cpt == 3)
+      producer_loop<3>(g, x, rdy, sp, misc, s_acopy, tid, lane, warp, rank, pair_in_grp, pairs_in_grp, n_units, n_pair_units);
+    else
+      producer_loop<4>(g, x, rdy, sp, misc, s_acopy, tid, lane, warp, rank, pair_in_grp, pairs_in_grp, n_units, n_pair_units);
   } else if (warp == MMA_WARP) {
     // =========================================== MMA ISSUER (rank 0 only) =======================
     if (rank == 0) {

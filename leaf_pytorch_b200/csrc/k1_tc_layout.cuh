@@ -106,9 +106,9 @@ constexpr int ZONE_INTS = 16;       // ints per channel group in the zone table:
 // Byte offsets of the kernel's dynamic shared memory regions.
 struct SmemPlan {
   int CL;          // halves per shifted copy: 8*127 + Kp
-  int LX;          // samples staged per tile: CL + 8
+  int LX;          // samples a tile's copies are cut from: CL + 8 (held in the producers' registers)
   int acb;         // bytes per copy
-  int off_w, off_acopy, off_st32, off_sth, off_stl, off_pw, off_red, off_out, off_misc, total;
+  int off_w, off_acopy, off_pw, off_red, off_out, off_misc, total;
 };
 
 // mode 0: forward (pooling partial buffers), mode 1: backward (small reduction scratch instead)
@@ -120,9 +120,6 @@ __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode =
   int off = 0;
   s.off_w = off;      off += (int)b_cta_bytes(CG, Kp);       // R1 | R2 of this CTA
   s.off_acopy = off;  off += 16 * s.acb;
-  s.off_st32 = off;   off += s.LX * 4;
-  s.off_sth = off;    off += (s.LX * 2 + 15) / 16 * 16;
-  s.off_stl = off;    off += (s.LX * 2 + 15) / 16 * 16;
   s.off_pw = off;     off += (mode == 0) ? 2 * 8 * SL * (CG / 4) * 4 : 8 * 32 * 4;
   // forward: per epilogue warp a (CG/4 filters) x 33 float transpose buffer (generic tile-end row sums)
   s.off_red = (off + 15) / 16 * 16;
