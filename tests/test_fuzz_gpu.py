@@ -74,3 +74,26 @@ def test_random_geometry_gradients_match_oracle_autograd(seed):
     for k in O.PARAM_KEYS:
         err = scaled_err(leaves[k].grad.cpu().numpy().reshape(-1), want[k].numpy().reshape(-1))
         assert err < 1e-3, (k, err, F, K, H, B, T)
+
+
+@pytest.mark.parametrize("F,K,H", [(8, 1601, 480), (12, 1345, 400), (20, 2001, 700)])
+def test_long_windows_match_oracle(F, K, H):
+    """Windows of 84-125 ms: 3-4 copy chunks per producer thread, many k-steps per zone, small channel groups."""
+    import leaf_pytorch_b200.functional as LF
+    assert LF.tc_supported(F, K, H)
+    rng = np.random.Generator(np.random.PCG64(K))
+    B, T = 2, 9000
+    prm_np = {
+        "kernel": np.stack([np.sort(rng.uniform(0.02, 3.0, F)), rng.uniform(3.0, 250.0, F)], 1).astype(np.float32),
+        "pool_w": rng.uniform(0.2, 0.5, F).astype(np.float32), "pool_b": rng.uniform(0.0, 1.0, F).astype(np.float32),
+        "alpha": np.full(F, 0.96, np.float32), "delta": np.full(F, 2.0, np.float32),
+        "root": np.full(F, 2.0, np.float32), "ema_w": np.full(F, 0.04, np.float32)}
+    prm = {k: torch.from_numpy(v) for k, v in prm_np.items()}
+    x = torch.from_numpy((np.clip(rng.standard_normal((B, 1, T)), -4, 4) / 4).astype(np.float32))
+    ref = O.forward_f32(x, prm, K, H).numpy()
+    p = [prm[k].cuda() for k in ("kernel", "pool_w", "pool_b", "alpha", "delta", "root", "ema_w")]
+    for algo in ("tc", "tc_full", "fp32"):
+        spec = LF.LeafSpec(F=F, K=K, H=H, compression=True, algo=algo)
+        out, _ = LF.forward_raw(spec, x.cuda(), *p)
+        torch.cuda.synchronize()
+        assert_close(out.cpu().numpy(), ref, f"long window F={F} K={K} H={H} {algo}")
