@@ -322,6 +322,7 @@ def main():
             "executed_note": "3 fp16 products per fp32 product (hi/lo split), taps padded 401->416, times the share of "
                              "(channel, k-step) pairs the support pruning keeps (active channels per k-step below)",
             "pruning": None if not sched else {"executed_fraction": exec_frac, "active_channels_per_kstep": sched["active"],
+                                               "all_three_products_channels_per_kstep": sched["active_all_products"],
                                                "channels_per_group": sched["channels_per_group"]},
             "k1_ms": ms_k1, "k0_ms": ms_k0, "k2_ms": ms_k2, "launches_profiled": n_prof,
             "k1_sm_cycles": k1_cyc, "k1_sm_mhz_effective": (1e3 * k1_cyc / k1_ns) if k1_ns else None,
@@ -346,7 +347,8 @@ def main():
                        "batch_per_gpu": B, "samples_per_clip": T, "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": f"{N_ROTATE} rotating input batches ({N_ROTATE * B * T * 4 / 1e6:.0f} MB > 126 MB L2)",
                        "arithmetic": "fp16 hi/lo split operands (3 products), fp32 accumulate; ~2^-21 relative; "
-                                     "taps beyond 5.5 sigma of a filter skipped per 16-tap step (< 2.7e-7 of its peak)"},
+                                     "taps beyond 5.5 sigma of a filter skipped per 16-tap step (< 2.7e-7 of its peak), "
+                                     "beyond 3.7 sigma only the main product"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * T * 4,
                     "d2h_bytes_per_step": world * B * F * n_frames * 4, "ms_per_step": e2e_ms / steps,

@@ -50,8 +50,9 @@ extern "C" {
 
 /* Flag OR-ed into `algo`, forward tensor-core kernel only (testing / A-B measurement).  By default the kernel
  * skips, per k-step of 16 taps, the filters whose Gaussian envelope has decayed below exp(-5.5^2/2) = 2.7e-7 of its
- * peak over the whole k-step (|tau| > ceil(5.5 sigma)): the rounding level of the fp16 hi/lo split itself.  With
- * this flag every filter runs over all taps. */
+ * peak over the whole k-step (|tau| > ceil(5.5 sigma)): the rounding level of the fp16 hi/lo split itself; and beyond
+ * ceil(3.7 sigma) (envelope < 1.1e-3) it runs only the main product x_hi*W_hi, not the two 2^-11 correction products.
+ * With this flag every filter runs all three products over all taps. */
 #define LEAFK_TC_NOPRUNE 32
 
 /* Learnable parameters of the frontend, in the reference's state_dict layout.
@@ -181,11 +182,11 @@ int leafk_profile_k1_clock(const leafk_config* cfg, int B, int T, const void* wo
                            long long* cycles, long long* nanoseconds);
 
 /* Profiling / tests only (synchronous copy): the support-pruning schedule k0 wrote for the LAST forward that used
- * `workspace` with shapes (B,T).  zones[g*16 + 2*(L-1) + {0,1}] = first / last k-step (of n_ksteps 16-tap steps) on
- * which channel group g runs at least 16*L of its channels_per_group channels, L = 1..channels_per_group/16; the
- * tensor work of a k-step is proportional to its active channels. */
+ * `workspace` with shapes (B,T).  codes[g*n_ksteps + s] = (na1/16) | (na3/16) << 4 for channel group g and 16-tap
+ * k-step s: na1 of the group's channels_per_group channels run there, na3 <= na1 of them all three split products
+ * (the others only x_hi*W_hi).  The tensor work of a k-step is proportional to na1 + 2*na3. */
 int leafk_profile_tc_schedule(const leafk_config* cfg, int B, int T, const void* workspace, size_t workspace_bytes,
-                              int* n_groups, int* channels_per_group, int* n_ksteps, int* zones, int zones_capacity);
+                              int* n_groups, int* channels_per_group, int* n_ksteps, int* codes, int codes_capacity);
 
 /* Introspection used by tests / bench: kernels launched by this thread since the last reset. */
 long long leafk_launch_count(int reset);

@@ -35,8 +35,11 @@ struct BankConsts {
 // ascending (key, index) order, sm_na[s] = active channels of THIS filter's group at k-step s.
 struct TcPrune {
   int* perm;          // [groups][FG] (group, slot) -> filter index (>= F: padding)
-  int* zones;         // [groups][tc::ZONE_INTS]: {lo_L, hi_L} = k-steps with >= 16 L active channels, L = 1..CG/16
+  int* zones;         // [groups][tc::ZONE_INTS]: ints [0,16) {lo_L, hi_L} = k-steps with >= 16 L channels running,
+                      // L = 1..CG/16; ints [16,32) {na3 on the rising zone of level L, on its falling zone}
+  int* kcodes;        // [groups][Kp/16] (na1/16) | (na3/16) << 4 per k-step (profiling read-back)
   float c;            // support radius in sigmas; <= 0: no pruning
+  float c3;           // radius beyond which only the main product runs; <= 0: everywhere all products
 };
 
 __global__ void __launch_bounds__(128)
@@ -49,8 +52,10 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
   const size_t grp_bytes = tc::b_group_bytes(tc_cg, Kp);
   const int FG = tc_cg / 2, Fp = FG * tc_groups, ks = Kp / tc::KSTEP;
   float* sm_key = k0_smem;
-  int* sm_pos = reinterpret_cast<int*>(k0_smem + Fp);       // rank | first active k-step << 8 | last << 16 (ks <= 128)
-  int* sm_na = sm_pos + Fp;
+  int* sm_pos = reinterpret_cast<int*>(k0_smem + Fp);       // rank | first k-step inside 5.5 sigma << 16 | last << 24 (ks <= 128)
+  int* sm_r3 = sm_pos + Fp;                                  // first k-step inside 3.7 sigma | last << 8
+  int* sm_na1 = sm_r3 + Fp;                                  // per k-step: channels of this filter's group that run
+  int* sm_na3 = sm_na1 + ks;                                 //             channels that run all three products
   int my_pos = 0;
   if (w16 != nullptr) {
     for (int i = threadIdx.x; i < Fp; i += blockDim.x)
@@ -63,47 +68,81 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
         const float kj = sm_key[j];
         r += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
       }
-      int lo, hi;
+      int lo, hi, lo3, hi3;
       tc::kstep_range(ki, pr.c, K, Kp, &lo, &hi);
+      tc::kstep_range(ki, pr.c3, K, Kp, &lo3, &hi3);
+      if (lo3 < lo) lo3 = lo;                                // (c3 <= 0 or > c: never more than the channels that run)
+      if (hi3 > hi) hi3 = hi;
       sm_pos[i] = r | (lo << 16) | (hi << 24);
+      sm_r3[i] = lo3 | (hi3 << 8);
     }
     __syncthreads();
     my_pos = sm_pos[f < Fp ? f : 0] & 0xffff;
     const int my_grp = tc::group_of(my_pos, tc_groups);
     for (int s = threadIdx.x; s < ks; s += blockDim.x) {
-      int cnt = 0;
+      int cnt = 0, cnt3 = 0;
       for (int j = 0; j < Fp; ++j) {
-        const int v = sm_pos[j];
-        cnt += (tc::group_of(v & 0xffff, tc_groups) == my_grp && s >= ((v >> 16) & 0xff) && s <= ((v >> 24) & 0xff)) ? 1 : 0;
+        const int v = sm_pos[j], v3 = sm_r3[j];
+        const bool mine = tc::group_of(v & 0xffff, tc_groups) == my_grp;
+        cnt += (mine && s >= ((v >> 16) & 0xff) && s <= ((v >> 24) & 0xff)) ? 1 : 0;
+        cnt3 += (mine && s >= (v3 & 0xff) && s <= ((v3 >> 8) & 0xff)) ? 1 : 0;
       }
-      int nf = (cnt + 7) / 8 * 8;
+      int nf = (cnt + 7) / 8 * 8, nf3 = (cnt3 + 7) / 8 * 8;
       if (nf > FG || s == tc::first_kstep(Kp)) nf = FG;
-      sm_na[s] = 2 * nf;
+      if (nf3 > nf || s == tc::first_kstep(Kp)) nf3 = nf;
+      sm_na1[s] = 2 * nf;
+      sm_na3[s] = 2 * nf3;
     }
+    __syncthreads();
+    // Make na3 constant on every zone of constant na1 (a zone = one side of the middle k-step): the largest value
+    // inside the zone; where every channel runs (na1 = CG) every channel also runs all three products.  The issue
+    // loop of k1 then has one (na1, na3) pair per zone and no more zones than with one pruning level.
+    int na3_aligned = 0;
+    const int sf = tc::first_kstep(Kp);
+    if ((int)threadIdx.x < ks) {
+      const int s = threadIdx.x, n1 = sm_na1[s];
+      na3_aligned = n1;
+      if (n1 < tc_cg) {
+        na3_aligned = 0;
+        for (int t = (s < sf ? 0 : sf + 1); t < (s < sf ? sf : ks); ++t)
+          if (sm_na1[t] == n1 && sm_na3[t] > na3_aligned) na3_aligned = sm_na3[t];
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < ks) sm_na3[threadIdx.x] = na3_aligned;
     __syncthreads();
     if (f < Fp && blockIdx.y == 0) {
       if (threadIdx.x == 0) pr.perm[my_grp * FG + tc::slot_of(my_pos, tc_groups)] = f;
-      if (tc::slot_of(my_pos, tc_groups) == 0 && threadIdx.x < tc_cg / 16) {     // the group's first filter publishes the zone table
+      if (tc::slot_of(my_pos, tc_groups) == 0 && threadIdx.x < tc_cg / 16) {   // the group's first filter publishes the zone tables
         const int L = threadIdx.x + 1;
-        int lo = ks, hi = -1;
-        for (int s = 0; s < ks; ++s)
-          if (sm_na[s] >= 16 * L) { lo = s < lo ? s : lo; hi = s; }
+        int lo = ks, hi = -1, n3r = 0, n3f = 0;
+        for (int s = 0; s < ks; ++s) {
+          if (sm_na1[s] >= 16 * L) { lo = s < lo ? s : lo; hi = s; }
+          if (sm_na1[s] == 16 * L) { if (s < sf) n3r = sm_na3[s]; else n3f = sm_na3[s]; }
+        }
         pr.zones[my_grp * tc::ZONE_INTS + 2 * (L - 1)] = lo;
         pr.zones[my_grp * tc::ZONE_INTS + 2 * (L - 1) + 1] = hi;
+        pr.zones[my_grp * tc::ZONE_INTS + 16 + 2 * (L - 1)] = n3r;
+        pr.zones[my_grp * tc::ZONE_INTS + 16 + 2 * (L - 1) + 1] = n3f;
       }
+      // per-k-step schedule for the profiling read-back: (na1/16) | (na3/16) << 4
+      if (tc::slot_of(my_pos, tc_groups) == 0)
+        for (int s = threadIdx.x; s < ks; s += blockDim.x)
+          pr.kcodes[my_grp * ks + s] = (sm_na1[s] >> 4) | ((sm_na3[s] >> 4) << 4);
     }
   }
   // tensor-core image: taps of sorted channel c = 2*j + q of group grp, only where the k-step keeps the channel
   auto store_tc = [&](int k, int q, float scaled) {
     const int grp = tc::group_of(my_pos, tc_groups), j = tc::slot_of(my_pos, tc_groups), c = 2 * j + q;
-    const int na = sm_na[k / tc::KSTEP];
-    if (c < tc_cg - na) return;                        // outside the active suffix: never read by the MMAs
+    const int na1 = sm_na1[k / tc::KSTEP], na3 = sm_na3[k / tc::KSTEP];
+    if (c < tc_cg - na1) return;                       // outside the active suffix: never read by the MMAs
     uint8_t* gb = w16 + (size_t)grp * grp_bytes;
     const __half hi = __float2half_rn(scaled);
+    *reinterpret_cast<__half*>(gb + tc::p_hi_main(tc_cg, Kp, c, na1, na3, k)) = hi;
+    if (c < tc_cg - na3) return;                       // main product only
     const __half lo = __float2half_rn(scaled - __half2float(hi));
-    *reinterpret_cast<__half*>(gb + tc::p_hi_main(tc_cg, Kp, c, k)) = hi;
-    *reinterpret_cast<__half*>(gb + tc::p_lo_main(tc_cg, Kp, c, na, k)) = lo;
-    *reinterpret_cast<__half*>(gb + tc::p_hi_corr(tc_cg, Kp, c, na, k)) = hi;
+    *reinterpret_cast<__half*>(gb + tc::p_lo_main(tc_cg, Kp, c, na1, na3, k)) = lo;
+    *reinterpret_cast<__half*>(gb + tc::p_hi_corr(tc_cg, Kp, c, na3, k)) = hi;
   };
   if (f >= F) {                             // padded channels: zero taps in both layouts
     for (int k = k_of_thread; k < Kp; k += gridDim.y * blockDim.x) {
@@ -286,17 +325,17 @@ void launch_k0_bwd(const float* kernel, const float* pool_w, int F, int K, int K
 
 void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
                float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, int* tc_perm, int* tc_zones,
-               float prune_c, cudaStream_t stream) {
+               float prune_c, float prune_c3, cudaStream_t stream) {
   const BankConsts bc = make_consts(K);
   int nblk = C2p / 2;
   const int Fp = tc_cg * tc_groups / 2;
   if (w16 != nullptr && Fp > nblk) nblk = Fp;
-  const size_t smem = (w16 != nullptr) ? sizeof(float) * (2 * (size_t)Fp + Kp / tc::KSTEP) : 0;
+  const size_t smem = (w16 != nullptr) ? sizeof(float) * (3 * (size_t)Fp + 2 * (Kp / tc::KSTEP)) : 0;
   // one tap per thread: gridDim.y chunks of 128 taps (the kernel is latency-bound: sincosf + expf + scattered
   // 2-byte stores per tap; 40 blocks looping over 416 taps took 14 us)
   const dim3 grid((unsigned)nblk, (unsigned)((Kp + 127) / 128));
   k0_banks_kernel<<<grid, 128, smem, stream>>>(kernel, pool_w, bc, F, K, Kp, C2p, cprm, w32, g32, w16, tc_cg,
-                                               tc_groups, TcPrune{tc_perm, tc_zones, prune_c});
+                                               tc_groups, TcPrune{tc_perm, tc_zones, tc_zones + (size_t)tc_groups * tc::ZONE_INTS, prune_c, prune_c3});
 }
 
 }  // namespace leafk

@@ -121,7 +121,8 @@ struct TcReady {
 // (k1_tc_layout.cuh, "SUPPORT PRUNING").
 struct TcMap {
   const int* perm;      // [n_groups * CG/2] sorted position -> filter index (>= F: padding)
-  const int* zones;     // [n_groups][tc::ZONE_INTS] {lo_L, hi_L} for L = 1..CG/16: k-steps with >= 16 L active channels
+  const int* zones;     // [n_groups][tc::ZONE_INTS]: ints [0,16) {lo_L, hi_L}, L = 1..CG/16: k-steps with >= 16 L channels
+                        // running; ints [16,32) {na3 of level L's rising zone, of its falling zone}
 };
 
 struct TcBwdArgs {
@@ -134,33 +135,48 @@ struct TcBwdArgs {
 };
 
 // ---- pruned MMA issue (forward) ------------------------------------------------------------------------------
-// The active channel count na(s) is unimodal in the k-step s (nested, centred supports), so the k-steps split into
-// at most 2*CG/16 - 1 ZONES of constant na: level L (na >= 16 L) is active on the k-step interval [lo_L, hi_L],
-// intervals nested.  k0 publishes the bounds; the issuing warp makes them warp-uniform registers (redux) and runs
+// The active channel count na1(s) is unimodal in the k-step s (nested, centred supports), so the k-steps split into
+// at most 2*CG/16 - 1 ZONES of constant na1: level L (na1 >= 16 L) is active on the k-step interval [lo_L, hi_L],
+// intervals nested; k0 makes na3 (channels that run all three products) constant on every zone.  k0 publishes the bounds; the issuing warp makes them warp-uniform registers (redux) and runs
 // one short loop per zone with NA a compile-time constant: running descriptors advanced by immediates, i.e. two
 // 64-bit uniform adds per MMA like the unpruned loop.  (Measured alternatives: a per-k-step table in shared memory
 // cost ~18 R2UR and 190 cycles per k-step, a per-k-step switch with immediate offsets -- jump tables -- 340.)
 template <int CG, int NA>
 __device__ __forceinline__ void issue_zone(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b1, uint64_t b2, int s0,
-                                           int s1, uint32_t accumulate_first) {
-  uint64_t ah = a_hi + (uint64_t)(2 * s0), al = a_lo + (uint64_t)(2 * s0);
-  uint64_t bb1 = b1 + (uint64_t)(s0 * 2 * CG + (CG - NA)), bb2 = b2 + (uint64_t)(s0 * CG + (CG - NA) / 2);
-  const uint32_t dd = d + (uint32_t)(CG - NA);
+                                           int s1, int na3, uint32_t accumulate_first) {
+  // NA channels run (compile time), the last na3 <= NA of them all three products (zone-uniform run-time value):
+  // main MMA N = NA + na3 into columns [CG-NA, CG+na3), corr MMA N = na3 into [CG-na3, CG)
+  // running descriptors: only the low words (start address field, 16-byte units) move, and never carry
+  uint32_t ah = (uint32_t)a_hi + (uint32_t)(2 * s0), al = (uint32_t)a_lo + (uint32_t)(2 * s0);
+  uint32_t bb1 = (uint32_t)b1 + (uint32_t)(s0 * 2 * CG + (CG - NA)), bb2 = (uint32_t)b2 + (uint32_t)(s0 * CG + (CG - na3) / 2);
+  const uint32_t ahh = (uint32_t)(a_hi >> 32), alh = (uint32_t)(a_lo >> 32), b1h = (uint32_t)(b1 >> 32), b2h = (uint32_t)(b2 >> 32);
+  const uint32_t d1 = d + (uint32_t)(CG - NA), d2 = d + (uint32_t)(CG - na3);
+  const uint32_t id1 = idesc_f16(256, 0) | ((uint32_t)((NA + na3) >> 3) << 17);
+  const uint32_t id2 = idesc_f16(256, 0) | ((uint32_t)(na3 >> 3) << 17);
+  if (na3 > 0) {
 #pragma unroll 1
-  for (int s = s0; s < s1; ++s) {
-    mma_f16_ss_pair(dd, ah, bb1, idesc_f16(256, 2 * NA), (s > s0) ? 1u : accumulate_first);
-    mma_f16_ss_pair(dd, al, bb2, idesc_f16(256, NA), 1);
-    ah += 2; al += 2; bb1 += (uint64_t)(2 * CG); bb2 += (uint64_t)CG;
+    for (int s = s0; s < s1; ++s) {
+      mma_f16_ss_pair_w(d1, ah, ahh, bb1, b1h, id1, (s > s0) ? 1u : accumulate_first);   // x_hi * [W_hi | W_lo]
+      mma_f16_ss_pair_w(d2, al, alh, bb2, b2h, id2, 1);                                  // x_lo * W_hi
+      ah += 2; al += 2; bb1 += (uint32_t)(2 * CG); bb2 += (uint32_t)CG;
+    }
+  } else {
+#pragma unroll 1
+    for (int s = s0; s < s1; ++s) {
+      mma_f16_ss_pair_w(d1, ah, ahh, bb1, b1h, id1, (s > s0) ? 1u : accumulate_first);   // x_hi * W_hi only
+      ah += 2; bb1 += (uint32_t)(2 * CG);
+    }
   }
 }
-// zones outside the centre one, levels L = LV .. 1 (rising side [lo_L, lo_{L+1}), falling side (hi_{L+1}, hi_L])
+// zones outside the centre one, levels L = LV .. 1 (rising side [lo_L, lo_{L+1}), falling side (hi_{L+1}, hi_L]);
+// z3r / z3f: channels of the level's rising / falling zone that run all three products
 template <int CG, int LV>
 __device__ __forceinline__ void issue_outer_zones(uint32_t d, uint64_t a_hi, uint64_t a_lo, uint64_t b1, uint64_t b2,
-                                                  const int* zlo, const int* zhi) {
+                                                  const int* zlo, const int* zhi, const int* z3r, const int* z3f) {
   if constexpr (LV >= 1) {
-    issue_zone<CG, 16 * LV>(d, a_hi, a_lo, b1, b2, zlo[LV - 1], zlo[LV], 1);
-    issue_zone<CG, 16 * LV>(d, a_hi, a_lo, b1, b2, zhi[LV] + 1, zhi[LV - 1] + 1, 1);
-    issue_outer_zones<CG, LV - 1>(d, a_hi, a_lo, b1, b2, zlo, zhi);
+    issue_zone<CG, 16 * LV>(d, a_hi, a_lo, b1, b2, zlo[LV - 1], zlo[LV], z3r[LV - 1], 1);
+    issue_zone<CG, 16 * LV>(d, a_hi, a_lo, b1, b2, zhi[LV] + 1, zhi[LV - 1] + 1, z3f[LV - 1], 1);
+    issue_outer_zones<CG, LV - 1>(d, a_hi, a_lo, b1, b2, zlo, zhi, z3r, z3f);
   }
 }
 
@@ -380,13 +396,15 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       long long dbg_t[3] = {0, 0, 0};
 #endif
       constexpr int LMAX = CG / 16;
-      int zlo[LMAX], zhi[LMAX];
+      int zlo[LMAX], zhi[LMAX], z3r[LMAX], z3f[LMAX];
       if constexpr (MODE == 0) {
         const int* z = tm.zones + (size_t)grp * tc::ZONE_INTS;
 #pragma unroll
         for (int L = 0; L < LMAX; ++L) {
           zlo[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 2 * L));
           zhi[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 2 * L + 1));
+          z3r[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 16 + 2 * L));
+          z3f[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 16 + 2 * L + 1));
         }
       }
       int it = 0;
@@ -414,8 +432,8 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
           if constexpr (MODE == 0) {
             if (leader) {
               // centre zone first (every channel; its first MMA initialises all 2*CG accumulator columns)
-              issue_zone<CG, CG>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo[LMAX - 1], zhi[LMAX - 1] + 1, 0);
-              issue_outer_zones<CG, LMAX - 1>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo, zhi);
+              issue_zone<CG, CG>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo[LMAX - 1], zhi[LMAX - 1] + 1, CG, 0);
+              issue_outer_zones<CG, LMAX - 1>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo, zhi, z3r, z3f);
               mma_commit_pair(&misc->a_empty[p]);
               mma_commit_pair(&misc->acc_full[st]);
             }

@@ -16,24 +16,31 @@
 // critical path: 94 operand wavefronts per k-step instead of 124, ncu r01.)
 //
 //
-// SUPPORT PRUNING (forward bank only).  A Gabor filter's taps beyond |tau| > R_f = ceil(c * sigma_f) are below
-// exp(-c^2/2) of its peak (c = 5.5: 2.7e-7, the level of the fp16 hi/lo split itself), so k-steps whose 16 taps
-// all lie outside [-R_f, R_f] contribute nothing for filter f.  k0 sorts the filters by width (ascending; padding
-// filters first), deals the sorted list round-robin to the channel groups, and for every (group, k-step) finds
-//   na[g][s] = 2 * (number of filters of the group, rounded up to 8, that are still inside their support)
-// -- the active channels are always the LAST na columns of the group's sorted order, and na is unimodal in s, so
-// it is published as nested k-step intervals: level L (na >= 16 L) is active on [lo_L, hi_L], L = 1..CG/16.  The MMAs of k-step s then
-// run with N = 2*na (main) and N = na (corr) and accumulate into columns [CG-na, CG+na) / [CG-na, CG):
-//   main, CTA0 rows [CG-na, CG)          hi of sorted channels CG-na .. CG-1          (row = channel)
-//   main, CTA1 rows [CG-na, CG)          lo halves in REVERSED filter order: D column CG+i holds the lo product
-//                                        of channel lo_channel(i) = 2*(FG-1 - i/2) + i%2, stored at row CG-na+i,
-//                                        so the lo product of a channel lands in the same column for every na
-//   corr, CTA0 rows [CG/2-na/2, CG/2)    hi of channels CG-na .. CG-na/2-1            (row = c - CG/2 + na/2)
-//   corr, CTA1 rows [CG/2-na/2, CG/2)    hi of channels CG-na/2 .. CG-1               (row = c - CG/2)
-// (one descriptor start offset serves both CTAs of the pair).  The middle k-step first_kstep(Kp) (|tau| <= 16 for
-// some tap: inside every real filter's support) is always run with na = CG and is issued first with
-// accumulate = 0, so every accumulator column is initialised.  With na = CG
-// everywhere this is the unpruned layout up to the order of the lo columns.
+// SUPPORT PRUNING (forward bank only), two levels.  Taps of filter f beyond |tau| > ceil(5.5 sigma_f) are below
+// exp(-5.5^2/2) = 2.7e-7 of its peak (the level of the fp16 hi/lo split itself): k-steps whose 16 taps all lie
+// outside contribute nothing for f.  And the two CORRECTION products (x_hi*W_lo, x_lo*W_hi; 2^-11 of the main one)
+// are only needed where the taps themselves are not small: beyond ceil(3.7 sigma_f) the envelope is below 1.1e-3, the
+// dropped terms below 5e-7 of peak*|x| (a 7e-8 relative error of y for broadband input).  k0 sorts the filters by width
+// (ascending; padding filters first), deals the sorted list round-robin to the channel groups, and for every
+// (group, k-step) finds
+//   na1[g][s] = 2 * (filters of the group, rounded up to 8, inside 5.5 sigma)   channels that run at all
+//   na3[g][s] = 2 * (filters of the group, rounded up to 8, inside 3.7 sigma)   channels that run all 3 products
+// -- always the LAST na1 / na3 columns of the group's sorted order, na3 <= na1, both unimodal in s.  na1 is published
+// as nested k-step intervals (level L, na1 >= 16 L, is active on [lo_L, hi_L], L = 1..CG/16); na3 is rounded up to
+// its largest value inside every zone of constant na1 (and to CG where na1 = CG), so that the issue loop of k1 has
+// one (na1, na3) pair per zone, and published per level and side.  The MMAs of k-step s run
+// with N = na1 + na3 (main, A = x_hi) into accumulator columns [CG-na1, CG+na3) and N = na3 (corr, A = x_lo) into
+// [CG-na3, CG).  With h = (na1+na3)/2 rows of B from each CTA of the pair and ONE descriptor start offset for both:
+//   main, CTA0 rows [CG-na1, CG-na1+h)   hi of sorted channels CG-na1 .. CG-na1+h-1            (row = channel)
+//   main, CTA1 rows [CG-na1, CG-h)       hi of the remaining channels CG-na1+h .. CG-1         (row = channel - h)
+//         CTA1 rows [CG-h, CG-h+na3)     lo halves in REVERSED filter order: D column CG+i holds the lo product of
+//                                        channel lo_channel(i) = 2*(FG-1 - i/2) + i%2, so the lo product of a
+//                                        channel lands in the same column for every (na1, na3)
+//   corr, CTA0 rows [CG/2-na3/2, CG/2)   hi of channels CG-na3 .. CG-na3/2-1            (row = c - CG/2 + na3/2)
+//   corr, CTA1 rows [CG/2-na3/2, CG/2)   hi of channels CG-na3/2 .. CG-1                (row = c - CG/2)
+// The middle k-step first_kstep(Kp) (|tau| <= 16 for some tap: inside every real filter's support) always runs with
+// na1 = na3 = CG and is issued first with accumulate = 0, so every accumulator column is initialised.  With
+// na1 = na3 = CG everywhere this is the unpruned layout up to the order of the lo columns.
 //
 // A operand = NOT materialised.  For phase p (0..7) a linear fp16 copy of the scaled sample window,
 // shifted by p samples, sits in shared memory: copy_p[i] = x~[ts - padL + p + i].  The descriptor
@@ -71,16 +78,23 @@ __host__ __device__ inline size_t g_hi_corr(int CG, int Kp, int c, int k) {
 }
 
 // ---- pruned forward layout: byte offsets inside a group's global image for sorted channel c = 2*j + ri -------
-// (FG = CG/2 filters per group, j = sorted position in the group, na = active channels of the k-step, k = tap)
-__host__ __device__ inline size_t p_hi_main(int CG, int Kp, int c, int k) { return region_offset(CG, c, k); }
-__host__ __device__ inline size_t p_lo_main(int CG, int Kp, int c, int na, int k) {
-  const int FG = CG / 2, j = c >> 1, ri = c & 1;
-  const int i = 2 * (FG - 1 - j) + ri;                      // lo column (relative to CG) of this channel
-  return r1_bytes(CG, Kp) + region_offset(CG, CG - na + i, k);
+// (FG = CG/2 filters per group, j = sorted position in the group, na1 / na3 = active channels of the k-step, k = tap)
+__host__ __device__ inline size_t p_hi_main(int CG, int Kp, int c, int na1, int na3, int k) {
+  const int h = (na1 + na3) / 2;
+  if (c < CG - na1 + h) return region_offset(CG, c, k);                       // CTA0
+  return r1_bytes(CG, Kp) + region_offset(CG, c - h, k);                       // CTA1, ahead of its lo rows
 }
-__host__ __device__ inline size_t p_hi_corr(int CG, int Kp, int c, int na, int k) {
+__host__ __device__ inline int lo_column(int CG, int c) {                      // lo column (relative to CG) of channel c
+  const int FG = CG / 2, j = c >> 1, ri = c & 1;
+  return 2 * (FG - 1 - j) + ri;
+}
+__host__ __device__ inline size_t p_lo_main(int CG, int Kp, int c, int na1, int na3, int k) {
+  const int h = (na1 + na3) / 2;
+  return r1_bytes(CG, Kp) + region_offset(CG, CG - h + lo_column(CG, c), k);
+}
+__host__ __device__ inline size_t p_hi_corr(int CG, int Kp, int c, int na3, int k) {
   const int h = CG / 2;
-  if (c < CG - na / 2) return 2 * r1_bytes(CG, Kp) + region_offset(h, c - h + na / 2, k);
+  if (c < CG - na3 / 2) return 2 * r1_bytes(CG, Kp) + region_offset(h, c - h + na3 / 2, k);
   return 2 * r1_bytes(CG, Kp) + r2_bytes(CG, Kp) + region_offset(h, c - h, k);
 }
 // k-steps [lo, hi] that hold a tap inside the support |tau| <= ceil(c * sigma) of a filter of width sigma
@@ -93,7 +107,8 @@ __host__ __device__ inline void kstep_range(float sigma, float c, int K, int Kp,
   const int k0 = kc - R < 0 ? 0 : kc - R, k1 = kc + R > K - 1 ? K - 1 : kc + R;
   *lo = k0 / KSTEP; *hi = k1 / KSTEP;
 }
-constexpr float PRUNE_C = 5.5f;      // default support radius in units of sigma
+constexpr float PRUNE_C = 5.5f;      // support radius in units of sigma: beyond it a filter's taps are skipped
+constexpr float PRUNE_C3 = 3.7f;     // beyond it only the main product x_hi*W_hi runs (no lo / correction products)
 // k-step the forward kernel issues first (accumulate = 0): k0 keeps every channel of every group active there
 __host__ __device__ constexpr int first_kstep(int Kp) { return (Kp / KSTEP - 1) / 2; }
 // width rank (ascending) -> channel group and slot inside it: the ranks are DEALT to the groups round-robin, so
@@ -101,7 +116,8 @@ __host__ __device__ constexpr int first_kstep(int Kp) { return (Kp / KSTEP - 1) 
 // slots of a group are still in ascending width
 __host__ __device__ inline int group_of(int rank, int n_groups) { return rank % n_groups; }
 __host__ __device__ inline int slot_of(int rank, int n_groups) { return rank / n_groups; }
-constexpr int ZONE_INTS = 16;       // ints per channel group in the zone table: {lo_L, hi_L}, L = 1..CG/16 <= 6
+constexpr int ZONE_INTS = 32;       // ints per channel group in the zone table: [0,16) {lo_L, hi_L} of na1, L = 1..CG/16 <= 6;
+                                    // [16,32) {na3 on level L's rising zone, on its falling zone}
 
 // Byte offsets of the kernel's dynamic shared memory regions.
 struct SmemPlan {
@@ -129,7 +145,7 @@ __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode =
   s.off_out = (s.off_out + 15) / 16 * 16;
   s.off_misc = s.off_out + ((mode == 0) ? SL * (CG / 2) * 16 : 0);
   s.off_misc = (s.off_misc + 15) / 16 * 16;
-  s.total = s.off_misc + 512;
+  s.total = s.off_misc + 1024;
   return s;
 }
 

@@ -13,7 +13,7 @@ namespace leafk {
 // k0_banks.cu
 void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
                float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, int* tc_perm, int* tc_zones,
-               float prune_c, cudaStream_t stream);
+               float prune_c, float prune_c3, cudaStream_t stream);
 // k1_fp32.cu
 cudaError_t launch_k1_fp32(const Geom& g, const float* x, const float* w32, const float* g32,
                            float* ppart, cudaStream_t stream);
@@ -116,7 +116,7 @@ static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace
   w->off_w32 = off;  off += align256(sizeof(float) * (size_t)g.Kp * g.C2p);
   w->off_g32 = off;  off += align256(sizeof(float) * (size_t)g.K * g.F);
   w->off_w16 = off;  off += align256(tc::b_group_bytes(*tc_cg, g.Kp) * (size_t)*tc_groups);
-  w->off_tcmap = off; off += align256(sizeof(int) * (size_t)*tc_groups * (*tc_cg / 2 + tc::ZONE_INTS));
+  w->off_tcmap = off; off += align256(sizeof(int) * (size_t)*tc_groups * (*tc_cg / 2 + tc::ZONE_INTS + g.Kp / tc::KSTEP));
   w->off_ppart = off;
   const int sl32 = (F32_TILE + g.K - 2) / g.H + 1, sltc = (TC_TILE + g.K - 2) / g.H + 1;
   size_t a = (size_t)max_tiles_fp32 * sl32, b = (size_t)max_tiles_tc * sltc;
@@ -202,10 +202,11 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   int* tc_perm = (int*)(base + w.off_tcmap);
   int* tc_zones = tc_perm + (size_t)tc_groups * (tc_cg / 2);
   const float prune_c = (cfg->algo & LEAFK_TC_NOPRUNE) ? 0.f : tc::PRUNE_C;
+  const float prune_c3 = (cfg->algo & LEAFK_TC_NOPRUNE) ? 0.f : tc::PRUNE_C3;
 
   prof_mark(0, stream);
   launch_k0(prm->kernel, prm->pool_w, g.F, g.K, g.Kp, g.C2p, cprm, w32, g32,
-            algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, tc_perm, tc_zones, prune_c, stream);
+            algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, tc_perm, tc_zones, prune_c, prune_c3, stream);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0 launch: %s", cudaGetErrorString(err));
   prof_mark(1, stream);
@@ -505,8 +506,8 @@ int leafk_profile_k1_clock(const leafk_config* cfg, int B, int T, const void* wo
 }
 
 int leafk_profile_tc_schedule(const leafk_config* cfg, int B, int T, const void* workspace, size_t workspace_bytes,
-                              int* n_groups, int* channels_per_group, int* n_ksteps, int* zones, int zones_capacity) {
-  if (!cfg || !workspace || !n_groups || !channels_per_group || !n_ksteps || !zones)
+                              int* n_groups, int* channels_per_group, int* n_ksteps, int* codes, int codes_capacity) {
+  if (!cfg || !workspace || !n_groups || !channels_per_group || !n_ksteps || !codes)
     return fail(LEAFK_EINVAL, "null pointer argument");
   const int N = leafk_num_frames(T, cfg->K, cfg->H);
   Geom g;
@@ -517,11 +518,12 @@ int leafk_profile_tc_schedule(const leafk_config* cfg, int B, int T, const void*
   int cg, ng;
   carve(g, 0, g.n_tiles, &w, &cg, &ng);
   if (w.total > workspace_bytes) return fail(LEAFK_EWORKSPACE, "workspace %zu bytes < %zu needed", workspace_bytes, w.total);
-  if (zones_capacity < ng * tc::ZONE_INTS) return fail(LEAFK_EINVAL, "zones_capacity %d < %d", zones_capacity, ng * tc::ZONE_INTS);
-  const int* dev = (const int*)((const uint8_t*)workspace + w.off_tcmap) + (size_t)ng * (cg / 2);
-  cudaError_t e = cudaMemcpy(zones, dev, sizeof(int) * (size_t)ng * tc::ZONE_INTS, cudaMemcpyDeviceToHost);   // synchronous: profiling only
+  const int ks = g.Kp / tc::KSTEP;
+  if (codes_capacity < ng * ks) return fail(LEAFK_EINVAL, "codes_capacity %d < %d", codes_capacity, ng * ks);
+  const int* dev = (const int*)((const uint8_t*)workspace + w.off_tcmap) + (size_t)ng * (cg / 2) + (size_t)ng * tc::ZONE_INTS;
+  cudaError_t e = cudaMemcpy(codes, dev, sizeof(int) * (size_t)ng * ks, cudaMemcpyDeviceToHost);   // synchronous: profiling only
   if (e != cudaSuccess) return fail(LEAFK_ECUDA, "schedule read: %s", cudaGetErrorString(e));
-  *n_groups = ng; *channels_per_group = cg; *n_ksteps = g.Kp / tc::KSTEP;
+  *n_groups = ng; *channels_per_group = cg; *n_ksteps = ks;
   return LEAFK_OK;
 }
 

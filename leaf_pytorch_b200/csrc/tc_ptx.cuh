@@ -114,6 +114,19 @@ __device__ __forceinline__ void mma_f16_ss_pair(uint32_t d_tmem, uint64_t adesc,
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors given as (low word, high word): the running descriptors of an issue loop only ever change in the
+// low word (start address field), so advancing one is a single 32-bit uniform add instead of an add-with-carry pair
+__device__ __forceinline__ void mma_f16_ss_pair_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // completion of all prior MMAs -> arrive on `bar` (same offset) in BOTH CTAs
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"

@@ -285,7 +285,8 @@ def k1_clock_probe(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root
 
 def tc_schedule(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w):
     """Run one forward and read back the support-pruning schedule of the tensor-core kernel (profiling / tests).
-    Returns dict(n_groups, channels_per_group, n_ksteps, active=[per group: list of active channels per k-step],
+    Returns dict(n_groups, channels_per_group, n_ksteps, active=[per group: channels running per k-step],
+    active_all_products=[per group: channels running all three split products per k-step],
     executed_fraction = executed / unpruned tensor work)."""
     L = N.lib()
     x = _check_input(x)
@@ -301,21 +302,19 @@ def tc_schedule(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, e
                                 _stream_ptr(x.device)), "leafk_forward")
         torch.cuda.synchronize(x.device)
         ng, cg, ks = C.c_int(0), C.c_int(0), C.c_int(0)
-        zones = (C.c_int * (64 * 16))()
+        codes = (C.c_int * (64 * 128))()
         N.check(L.leafk_profile_tc_schedule(C.byref(cfg), B, T, _ptr(ws), ws_bytes, C.byref(ng), C.byref(cg), C.byref(ks),
-                                            zones, 64 * 16), "leafk_profile_tc_schedule")
+                                            codes, 64 * 128), "leafk_profile_tc_schedule")
     del keep
-    active = []
-    for g in range(ng.value):
-        na = [0] * ks.value
-        for lv in range(cg.value // 16):
-            lo, hi = zones[g * 16 + 2 * lv], zones[g * 16 + 2 * lv + 1]
-            for s in range(lo, hi + 1):
-                na[s] += 16
-        active.append(na)
-    total = sum(sum(a) for a in active)
+
+    def table(g, shift):
+        return [16 * ((codes[g * ks.value + s] >> shift) & 15) for s in range(ks.value)]
+    active = [table(g, 0) for g in range(ng.value)]          # channels that run (main product)
+    active3 = [table(g, 4) for g in range(ng.value)]         # channels that run all three products
+    total = sum(sum(a) for a in active) + 2 * sum(sum(a) for a in active3)
     return {"n_groups": ng.value, "channels_per_group": cg.value, "n_ksteps": ks.value, "active": active,
-            "executed_fraction": total / float(ng.value * cg.value * ks.value)}
+            "active_all_products": active3,
+            "executed_fraction": total / float(3 * ng.value * cg.value * ks.value)}
 
 
 def profile_begin() -> None:
