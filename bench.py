@@ -255,7 +255,7 @@ def main():
         # its own input H2D from pinned memory and reads its own result D2H; the copies of neighbouring steps
         # overlap the kernels.
         def pipelined(hosts, dtype):
-            pipe = L.HostPipeline(fe, B, T, depth=2, n_slices=8, input_dtype=dtype)
+            pipe = L.HostPipeline(fe, B, T, depth=2, n_slices=2, input_dtype=dtype)
             outs = [torch.empty((B, F, n_frames), dtype=torch.float32).pin_memory() for _ in range(2)]
             pipe.result(pipe.submit(hosts[0], outs[0]))
             pipe.result(pipe.submit(hosts[1 % len(hosts)], outs[1]))
@@ -353,7 +353,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * B * T * 4,
                     "d2h_bytes_per_step": world * B * F * n_frames * 4, "ms_per_step": e2e_ms / steps,
                     "api": "HostPipeline.submit/result -> leafk_forward_host_async: pinned host in/out, 2 batches in flight, "
-                           "H2D in 8 slices with ready flags feeding one persistent launch per batch"},
+                           "H2D in 2 slices with ready flags feeding one persistent launch per batch"},
             "e2e_sync": {"value": audio_s_step * steps / (sync_ms * 1e-3), "unit": UNIT, "ms_per_step": sync_ms / steps,
                          "api": "Leaf.forward_host (one synchronous call per batch: H2D slices + flags, kernels, D2H)"},
             "e2e_pcm16": {"value": audio_s_step * steps / (pcm_ms * 1e-3), "unit": UNIT,

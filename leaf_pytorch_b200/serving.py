@@ -27,7 +27,7 @@ class _Set:
 
 
 class HostPipeline:
-    def __init__(self, leaf, batch: int, n_samples: int, depth: int = 2, n_slices: int = 8,
+    def __init__(self, leaf, batch: int, n_samples: int, depth: int = 2, n_slices: int = 2,
                  input_dtype: torch.dtype = torch.float32, device=None):
         self.lib = N.lib()
         self.leaf = leaf

@@ -79,3 +79,14 @@ def test_shard_bounds_cover_and_balance():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_bounds(4, 2, 2)
+
+
+def test_numa_binding_helpers_are_safe_without_a_gpu():
+    """bind_to_gpu_numa_node never raises and changes nothing when the topology cannot be read (no GPU here)."""
+    import os
+    from leaf_pytorch_b200 import distributed as D
+    assert D._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert D._parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    assert D.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
