@@ -359,3 +359,62 @@ def test_support_pruning_worst_cases_against_oracle():
         assert_close(outs[algo], ref, f"pruning worst case / {algo}")
     sch = LF.tc_schedule(LF.LeafSpec(F=F, K=K, H=H, compression=True, algo="tc"), x.cuda(), *p)
     assert sch["executed_fraction"] < 0.95
+
+
+def _expected_schedule(sigma, F, K, cg, n_groups, c1=5.5, c3=3.7):
+    """Host restatement of k0's pruning schedule (k1_tc_layout.cuh): per group and 16-tap k-step the channels that
+    run (inside ceil(5.5 sigma), filters rounded up to 8) and those that run all three products (inside
+    ceil(3.7 sigma), then made constant per zone of constant na1 and side of the middle k-step)."""
+    import math
+    Kp = (K + 15) // 16 * 16
+    ks, FG, Fp, kc = Kp // 16, cg // 2, (cg // 2) * n_groups, K // 2
+    key = [float(sigma[i]) if i < F else -1.0 for i in range(Fp)]
+    rank = [sum(1 for j in range(Fp) if key[j] < key[i] or (key[j] == key[i] and j < i)) for i in range(Fp)]
+
+    def rng(s, c):
+        if s < 0:
+            return 1, 0
+        R = min(K, int(math.ceil(np.float32(c) * np.float32(s))))
+        return max(0, kc - R) // 16, min(K - 1, kc + R) // 16
+    sf = (ks - 1) // 2
+    na1 = [[0] * ks for _ in range(n_groups)]
+    na3 = [[0] * ks for _ in range(n_groups)]
+    for g in range(n_groups):
+        members = [i for i in range(Fp) if rank[i] % n_groups == g]
+        for s in range(ks):
+            c1n = sum(1 for i in members if rng(key[i], c1)[0] <= s <= rng(key[i], c1)[1])
+            c3n = sum(1 for i in members if max(rng(key[i], c3)[0], rng(key[i], c1)[0]) <= s <= min(rng(key[i], c3)[1], rng(key[i], c1)[1]))
+            nf = min(FG, (c1n + 7) // 8 * 8)
+            nf3 = min(nf, (c3n + 7) // 8 * 8)
+            if s == sf:
+                nf = nf3 = FG
+            na1[g][s], na3[g][s] = 2 * nf, 2 * nf3
+        al = list(na3[g])
+        for s in range(ks):
+            if na1[g][s] == cg:
+                al[s] = cg
+            else:
+                side = range(0, sf) if s < sf else range(sf + 1, ks)
+                al[s] = max([na3[g][t] for t in side if na1[g][t] == na1[g][s]] + [0])
+        na3[g] = al
+    return na1, na3
+
+
+@pytest.mark.parametrize("F,seed", [(40, 0), (40, 1), (80, 2), (64, 3), (20, 4), (47, 5)])
+def test_pruning_schedule_matches_host_restatement(F, seed):
+    import leaf_pytorch_b200 as L
+    import leaf_pytorch_b200.functional as LF
+    fe = L.Leaf(n_filters=F, algo="tc").cuda()
+    rng = np.random.Generator(np.random.PCG64(900 + seed))
+    if seed:                                              # seed 0: the default mel initialisation
+        with torch.no_grad():
+            k = fe._complex_conv._kernel
+            k[:, 1] = torch.from_numpy(rng.uniform(1.0, 120.0, F).astype(np.float32)).to(k.device)
+    x = (torch.randn(2, 1, 3000, generator=torch.Generator().manual_seed(seed)).clamp_(-4, 4) / 4).cuda()
+    sch = LF.tc_schedule(fe.spec, x, *[None if q is None else q.detach() for q in fe._param_tuple()])
+    sig = fe._complex_conv._kernel.detach()[:, 1].cpu().numpy().astype(np.float32)
+    lo, hi = np.float32(4 * np.sqrt(2 * np.log(2.0)) / np.pi), np.float32(401 * np.sqrt(2 * np.log(2.0)) / np.pi)
+    sig = np.clip(sig, lo, hi)
+    na1, na3 = _expected_schedule(sig, F, 401, sch["channels_per_group"], sch["n_groups"])
+    assert sch["active"] == na1
+    assert sch["active_all_products"] == na3
