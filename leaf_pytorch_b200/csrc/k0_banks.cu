@@ -47,6 +47,9 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
                 int F, int K, int Kp, int C2p, float* __restrict__ cprm, float* __restrict__ w32,
                 float* __restrict__ g32, uint8_t* __restrict__ w16, int tc_cg, int tc_groups, TcPrune pr) {
   extern __shared__ float k0_smem[];
+  // programmatic dependent launch: the consumer (K1) may be scheduled while this grid runs; it waits for this grid's
+  // completion (griddepcontrol.wait) before it touches the banks
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int f = blockIdx.x;                 // filter (or a zero-padding channel pair when f >= F)
   const int k_of_thread = blockIdx.y * blockDim.x + threadIdx.x;   // one tap per thread, gridDim.y chunks of taps
   const size_t grp_bytes = tc::b_group_bytes(tc_cg, Kp);

@@ -36,6 +36,7 @@
 
 #include <cuda_fp16.h>
 #include <cstdio>
+#include <cstring>
 
 #ifndef LEAFK_EXP
 #define LEAFK_EXP 0      // timing experiments only (results wrong): 1 = no epilogue loads + arithmetic, 2 = producers skip the
@@ -349,6 +350,13 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   const int ksteps = g.Kp / KSTEP;
 
   // ---- one-time setup ---------------------------------------------------------------------------
+  // Programmatic dependent launch (forward): this grid may have been scheduled while the bank prologue k0 was still
+  // running -- wait for its completion before reading anything it wrote; and let the PCEN kernel be scheduled as soon
+  // as SMs free up at the tail of this grid (it waits for our completion itself).
+  if constexpr (MODE == 0) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   {
     // this CTA's bank regions: R1 (main MMA) then R2 (corr MMA), from the group's global image
     const uint8_t* gimg = w16 + (size_t)grp * b_group_bytes(CG, g.Kp);
@@ -815,8 +823,13 @@ static cudaError_t launch_inst_ks(const Geom& g, const float* x, const uint8_t* 
   cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   TcBwdArgs none{nullptr, nullptr, nullptr, 0, 0};
-  k1_tc_kernel<CG, NSLOT, 0, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, cprm, ppart, n_groups, none, rdy, tm);
-  return cudaGetLastError();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(tc::NTHREADS); lc.dynamicSmemBytes = (size_t)smem; lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // may start under the tail of k0 (see kernel)
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, k1_tc_kernel<CG, NSLOT, 0, KS>, g, x, w16, cprm, ppart, n_groups, none, rdy, tm);
 }
 template <int CG, int NSLOT>
 static cudaError_t launch_inst(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,

@@ -14,6 +14,7 @@
 // only HBM-bound stage of the path (~14 B per output element).
 #include "leafk_common.cuh"
 #include "k2_pcen_args.cuh"
+#include <cstring>
 
 namespace leafk {
 
@@ -26,6 +27,8 @@ __device__ __forceinline__ float pow_pos(float x, float y) { return exp2f(y * lo
 
 __global__ void __launch_bounds__(K2_WARPS * 32)
 k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, int tl_shift, unsigned long long hop_magic) {
+  // programmatic dependent launch: scheduled under the tail of the kernel that writes the partial sums
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rows = g.B * g.F;
   const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;       // clip length <= 2^30 (checked on the host)
@@ -137,8 +140,13 @@ cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cuda
   long long blocks = (rows + K2_WARPS - 1) / K2_WARPS;
   if (blocks > (1LL << 20)) blocks = 1LL << 20;
   const unsigned long long hop_magic = div_magic_of((unsigned)g.H);
-  k2_pcen_kernel<<<(unsigned)blocks, K2_WARPS * 32, 0, stream>>>(g, ppart, a, tl_shift, hop_magic);
-  return cudaGetLastError();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)blocks); lc.blockDim = dim3(K2_WARPS * 32); lc.dynamicSmemBytes = 0; lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, k2_pcen_kernel, g, ppart, a, tl_shift, hop_magic);
 }
 
 }  // namespace leafk
