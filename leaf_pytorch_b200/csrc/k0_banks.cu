@@ -40,6 +40,8 @@ struct TcPrune {
   int* kcodes;        // [groups][Kp/16] (na1/16) | (na3/16) << 4 per k-step (profiling read-back)
   float c;            // support radius in sigmas; <= 0: no pruning
   float c3;           // radius beyond which only the main product runs; <= 0: everywhere all products
+  int* done;          // [n_done] per-clip completion counters of K1 -> K2, zeroed here
+  int n_done;
 };
 
 __global__ void __launch_bounds__(128)
@@ -52,6 +54,10 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int f = blockIdx.x;                 // filter (or a zero-padding channel pair when f >= F)
   const int k_of_thread = blockIdx.y * blockDim.x + threadIdx.x;   // one tap per thread, gridDim.y chunks of taps
+  if (pr.done != nullptr)
+    for (int i = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < pr.n_done;
+         i += gridDim.x * gridDim.y * blockDim.x)
+      pr.done[i] = 0;
   const size_t grp_bytes = tc::b_group_bytes(tc_cg, Kp);
   const int FG = tc_cg / 2, Fp = FG * tc_groups, ks = Kp / tc::KSTEP;
   float* sm_key = k0_smem;
@@ -328,7 +334,7 @@ void launch_k0_bwd(const float* kernel, const float* pool_w, int F, int K, int K
 
 void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
                float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, int* tc_perm, int* tc_zones,
-               float prune_c, float prune_c3, cudaStream_t stream) {
+               float prune_c, float prune_c3, int* done, int n_done, cudaStream_t stream) {
   const BankConsts bc = make_consts(K);
   int nblk = C2p / 2;
   const int Fp = tc_cg * tc_groups / 2;
@@ -338,7 +344,7 @@ void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, i
   // 2-byte stores per tap; 40 blocks looping over 416 taps took 14 us)
   const dim3 grid((unsigned)nblk, (unsigned)((Kp + 127) / 128));
   k0_banks_kernel<<<grid, 128, smem, stream>>>(kernel, pool_w, bc, F, K, Kp, C2p, cprm, w32, g32, w16, tc_cg,
-                                               tc_groups, TcPrune{tc_perm, tc_zones, tc_zones + (size_t)tc_groups * tc::ZONE_INTS, prune_c, prune_c3});
+                                               tc_groups, TcPrune{tc_perm, tc_zones, tc_zones + (size_t)tc_groups * tc::ZONE_INTS, prune_c, prune_c3, done, n_done});
 }
 
 }  // namespace leafk

@@ -121,6 +121,7 @@ struct TcReady {
 // Forward only: the width-sorted channel order and the per-k-step active channel counts written by k0
 // (k1_tc_layout.cuh, "SUPPORT PRUNING").
 struct TcMap {
+  int* done;            // [B] per-clip completion counters for K2 (one increment per epilogue warp and stored tile)
   const int* perm;      // [n_groups * CG/2] sorted position -> filter index (>= F: padding)
   const int* zones;     // [n_groups][tc::ZONE_INTS]: ints [0,16) {lo_L, hi_L}, L = 1..CG/16: k-steps with >= 16 L channels
                         // running; ints [16,32) {na3 of level L's rising zone, of its falling zone}
@@ -496,6 +497,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
     const float centre = 0.5f * (float)(g.K - 1);
     const int n_last = g.n_begin + g.n_count - 1;
     float* red = s_red + (size_t)e * FPT * 33;          // this warp's transpose buffer (generic tile-end row sums)
+    int sig_b = -1;                                     // clip whose last stored tile K2 has not been told about yet
     const int red_fi = halving_index<FPT, 16>(lane);    // filter whose row sum the halving reduction leaves in this lane
     // output table of the tile-end store (slot fastest, the layout K2 reads); read back by the same threads only
     for (int idx = etid; idx < g.SL * (CG / 2); idx += EPI_WARPS * 32) {
@@ -573,6 +575,12 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_rank0(&misc->acc_empty[st]);
+        if (p == 1 && sig_b >= 0) {          // the previous tile's partial sums were stored a phase ago: publish them to K2
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicAdd(tm.done + sig_b, 1);
+          sig_b = -1;
+        }
 #if (LEAFK_EXP & 64)
         dbg_e[1] += clock64() - te1;
 #endif
@@ -665,9 +673,15 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
           dst[o.y] = scalbnf(s, -2 * (sx + o.z));
         }
       }
+      sig_b = (valid && tm.done != nullptr) ? b : -1;   // published off the critical path (phase 1 of the next tile)
 #if (LEAFK_EXP & 64)
       dbg_e[2] += clock64() - te2;
 #endif
+    }
+    if (sig_b >= 0) {
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(tm.done + sig_b, 1);
     }
 #if (LEAFK_EXP & 64)
     if (blockIdx.x == 0 && tid == 0)
@@ -844,7 +858,7 @@ static cudaError_t launch_bwd_inst_ks(const Geom& g, const float* x, const uint8
   cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 1, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (err != cudaSuccess) return err;
   k1_tc_kernel<CG, NSLOT, 1, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, nullptr, nullptr, n_groups, ba,
-                                                                       TcReady{nullptr, 1, nullptr}, TcMap{nullptr, nullptr});
+                                                                       TcReady{nullptr, 1, nullptr}, TcMap{nullptr, nullptr, nullptr});
   return cudaGetLastError();
 }
 template <int CG, int NSLOT>
@@ -897,10 +911,10 @@ static cudaError_t launch_cg(int nslot, const Geom& g, const float* x, const uin
 }
 
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
-                         int tc_cg, int tc_groups, const int* tc_perm, const int* tc_zones, cudaStream_t stream,
+                         int tc_cg, int tc_groups, const int* tc_perm, const int* tc_zones, int* done, cudaStream_t stream,
                          const int* ready, int clips_per_flag, long long* perf) {
   const TcReady rdy{ready, clips_per_flag < 1 ? 1 : clips_per_flag, perf};
-  const TcMap tm{tc_perm, tc_zones};
+  const TcMap tm{done, tc_perm, tc_zones};
   cudaError_t err;
   const int n_sm = sm_count(&err);
   if (err != cudaSuccess) return err;

@@ -27,8 +27,12 @@ __device__ __forceinline__ float pow_pos(float x, float y) { return exp2f(y * lo
 
 __global__ void __launch_bounds__(K2_WARPS * 32)
 k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, int tl_shift, unsigned long long hop_magic) {
-  // programmatic dependent launch: scheduled under the tail of the kernel that writes the partial sums
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // Programmatic dependent launch: this grid is scheduled under the tail of the kernel that writes the partial sums.
+  // After the tensor-core K1 it does not wait for that whole grid: K1 counts, per clip, the tiles whose partial sums are
+  // stored (release), and a row starts as soon as its clip is complete (acquire) -- clips finish in index order and
+  // the SMs whose CTAs have run out of tiles (a third of them idle through K1's last tile) take the early clips, so
+  // most of this kernel hides under K1's tail.  After any other producer: wait for the grid.
+  if (a.done == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rows = g.B * g.F;
   const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;       // clip length <= 2^30 (checked on the host)
@@ -37,6 +41,18 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
 
   for (int row = blockIdx.x * K2_WARPS + warp; row < rows; row += gridDim.x * K2_WARPS) {
     const int b = row / g.F, f = row - b * g.F;
+    if (a.done != nullptr) {
+      if (lane == 0) {
+        const int* flag = a.done + b;
+        int v;
+        unsigned spins = 0;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          if (v < a.done_target) { __nanosleep(100); if (++spins > (1u << 25)) __trap(); }   // bounded: a bug must not hang the GPU
+        } while (v < a.done_target);
+      }
+      __syncwarp();
+    }
     const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + (size_t)f * g.SL;
     float* orow = a.out + (size_t)b * a.ldo_b + (size_t)f * a.ldo_f;
     float* prow = a.saved_p ? a.saved_p + (size_t)b * a.ldo_b + (size_t)f * a.ldo_f : nullptr;
@@ -68,7 +84,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
             const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
             int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
             if (nf < g.n_begin) nf = g.n_begin;
-            s += __ldg(pbase + (size_t)i * tile_stride + (n - nf));
+            s += __ldcg(pbase + (size_t)i * tile_stride + (n - nf));   // written by a grid that may still be running: L2, not the read-only path
           }
           p[u] = s;
         }

@@ -14,5 +14,7 @@ struct PcenArgs {
   long long ldo_b, ldo_f;
   float pcen_floor, clamp_min;
   int compression;
+  const int* done;       // per-clip completion counters written by the tensor-core K1, or null (then the kernel waits
+  int done_target;       // for the whole preceding grid); a clip is ready at done[b] >= done_target
 };
 }  // namespace leafk

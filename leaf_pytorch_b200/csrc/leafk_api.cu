@@ -13,7 +13,7 @@ namespace leafk {
 // k0_banks.cu
 void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
                float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, int* tc_perm, int* tc_zones,
-               float prune_c, float prune_c3, cudaStream_t stream);
+               float prune_c, float prune_c3, int* done, int n_done, cudaStream_t stream);
 // k1_fp32.cu
 cudaError_t launch_k1_fp32(const Geom& g, const float* x, const float* w32, const float* g32,
                            float* ppart, cudaStream_t stream);
@@ -21,7 +21,7 @@ constexpr int F32_TILE = 512;
 // k1_tc.cu
 bool k1_tc_supported(const Geom& g, const char** why);
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm,
-                         float* ppart, int tc_cg, int tc_groups, const int* tc_perm, const int* tc_zones,
+                         float* ppart, int tc_cg, int tc_groups, const int* tc_perm, const int* tc_zones, int* done,
                          cudaStream_t stream, const int* ready, int clips_per_flag, long long* perf);
 constexpr int TC_TILE = 1024;
 // k2_pcen.cu
@@ -122,6 +122,7 @@ static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace
   size_t a = (size_t)max_tiles_fp32 * sl32, b = (size_t)max_tiles_tc * sltc;
   off += align256(sizeof(float) * (size_t)g.B * g.F * (a > b ? a : b));
   w->off_flags = off; off += 256;                      // 32 slice-ready flags (leafk_forward_host) + 2 perf counters
+  w->off_done = off;  off += align256(sizeof(int) * (size_t)g.B);
   w->total = off;
 }
 
@@ -203,10 +204,12 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   int* tc_zones = tc_perm + (size_t)tc_groups * (tc_cg / 2);
   const float prune_c = (cfg->algo & LEAFK_TC_NOPRUNE) ? 0.f : tc::PRUNE_C;
   const float prune_c3 = (cfg->algo & LEAFK_TC_NOPRUNE) ? 0.f : tc::PRUNE_C3;
+  int* done = (int*)(base + w.off_done);
 
   prof_mark(0, stream);
   launch_k0(prm->kernel, prm->pool_w, g.F, g.K, g.Kp, g.C2p, cprm, w32, g32,
-            algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, tc_perm, tc_zones, prune_c, prune_c3, stream);
+            algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, tc_perm, tc_zones, prune_c, prune_c3,
+            algo == LEAFK_ALGO_TC ? done : nullptr, g.B, stream);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0 launch: %s", cudaGetErrorString(err));
   prof_mark(1, stream);
@@ -214,7 +217,7 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   if (flags_out) *flags_out = flags;
   if (algo_out) *algo_out = algo;
   if (algo == LEAFK_ALGO_TC)
-    err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, tc_perm, tc_zones, stream,
+    err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, tc_perm, tc_zones, done, stream,
                        clips_per_flag > 0 ? flags : nullptr, clips_per_flag, g_prof_on ? (long long*)(flags + 32) : nullptr);
   else
     err = launch_k1_fp32(g, x_win, w32, g32, ppart, stream);
@@ -225,6 +228,8 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   a.ema_w = prm->ema_w; a.ema_in = ema_state_in; a.ema_out = ema_state_out; a.out = out;
   a.saved_p = saved_p; a.ldo_b = ldo_b; a.ldo_f = ldo_f; a.pcen_floor = cfg->pcen_floor;
   a.clamp_min = cfg->clamp_min; a.compression = cfg->compression;
+  a.done = (algo == LEAFK_ALGO_TC) ? done : nullptr;
+  a.done_target = g.n_tiles * tc_groups * 8;              // epilogue warps x tiles x channel groups of a clip
   err = launch_k2(g, ppart, a, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k2 launch: %s", cudaGetErrorString(err));
   prof_mark(3, stream);

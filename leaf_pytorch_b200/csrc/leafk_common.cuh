@@ -77,6 +77,8 @@ struct Workspace {
   size_t off_tcmap;  // int[Fp] sorted position -> filter, then int[groups][16] zone table (k1_tc_layout.cuh)
   size_t off_ppart;  // float[B][n_tiles][F][SL] partial pooled sums (slot fastest)
   size_t off_flags;  // int[64]      slice-ready flags of the host-pipelined forward
+  size_t off_done;   // int[B]       per clip: epilogue warps of K1 that have stored a tile of it (K2 starts a clip at
+                     //              n_tiles * n_groups * 8, see k2_pcen.cu)
   size_t total;
 };
 
