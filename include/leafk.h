@@ -55,6 +55,11 @@ extern "C" {
  * With this flag every filter runs all three products over all taps. */
 #define LEAFK_TC_NOPRUNE 32
 
+/* Flag OR-ed into `algo`, forward calls: the caller guarantees that `workspace` still holds what the bank prologue
+ * wrote during an earlier forward with the SAME parameters, config and workspace (e.g. the previous chunk of a
+ * chunked long clip, leafk_forward_window): the prologue kernel is skipped. */
+#define LEAFK_REUSE_BANKS 64
+
 /* Learnable parameters of the frontend, in the reference's state_dict layout.
  *   kernel   (F,2)  _complex_conv._kernel      reference convolution.py:58
  *   pool_w   (F)    _pooling.weights (1,1,F,1) reference pooling.py:18-20

@@ -18,6 +18,7 @@ ALGO_AUTO, ALGO_FP32, ALGO_TC = 0, 1, 2
 TC_NOPRUNE = 32        # LEAFK_TC_NOPRUNE: every filter over all taps (no support pruning of the k-steps)
 ALGOS = {"auto": ALGO_AUTO, "fp32": ALGO_FP32, "tc": ALGO_TC, "tc_full": ALGO_TC | TC_NOPRUNE}
 BWD_2PRODUCT = 16
+REUSE_BANKS = 64       # LEAFK_REUSE_BANKS: the workspace still holds the banks of the same parameters (chunked clips)
 
 SYMBOLS = (
     "leafk_version", "leafk_last_error", "leafk_num_frames", "leafk_same_padding",

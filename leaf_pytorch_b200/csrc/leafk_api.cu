@@ -207,11 +207,18 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   int* done = (int*)(base + w.off_done);
 
   prof_mark(0, stream);
-  launch_k0(prm->kernel, prm->pool_w, g.F, g.K, g.Kp, g.C2p, cprm, w32, g32,
-            algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, tc_perm, tc_zones, prune_c, prune_c3,
-            algo == LEAFK_ALGO_TC ? done : nullptr, g.B, stream);
-  cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0 launch: %s", cudaGetErrorString(err));
+  cudaError_t err;
+  if (cfg->algo & LEAFK_REUSE_BANKS) {
+    // banks, sort and schedule are still in the workspace (same parameters): only the per-clip counters are reset
+    err = (algo == LEAFK_ALGO_TC) ? cudaMemsetAsync(done, 0, sizeof(int) * (size_t)g.B, stream) : cudaSuccess;
+    if (err != cudaSuccess) return fail(LEAFK_ECUDA, "counter reset: %s", cudaGetErrorString(err));
+  } else {
+    launch_k0(prm->kernel, prm->pool_w, g.F, g.K, g.Kp, g.C2p, cprm, w32, g32,
+              algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, tc_perm, tc_zones, prune_c, prune_c3,
+              algo == LEAFK_ALGO_TC ? done : nullptr, g.B, stream);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0 launch: %s", cudaGetErrorString(err));
+  }
   prof_mark(1, stream);
   int* flags = (int*)(base + w.off_flags);
   if (flags_out) *flags_out = flags;

@@ -30,8 +30,8 @@ class LeafSpec:
     clamp_min: float = CLAMP_MIN
     fast_backward: bool = False      # LEAFK_BWD_2PRODUCT: drop the x_lo*W_hi product in the backward correlations
 
-    def config(self, input_dtype=torch.float32) -> N.Config:
-        algo = N.ALGOS[self.algo] | (N.BWD_2PRODUCT if self.fast_backward else 0)
+    def config(self, input_dtype=torch.float32, reuse_banks: bool = False) -> N.Config:
+        algo = N.ALGOS[self.algo] | (N.BWD_2PRODUCT if self.fast_backward else 0) | (N.REUSE_BANKS if reuse_banks else 0)
         return N.Config(self.F, self.K, self.H, self.pcen_floor, self.clamp_min, int(self.compression),
                         algo, 1 if input_dtype == torch.int16 else 0)
 
@@ -109,15 +109,31 @@ def forward_raw(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, e
     return out, saved
 
 
+def workspace_bytes(spec: LeafSpec, B: int, n_frames: int, input_dtype=torch.float32) -> int:
+    cfg = spec.config(input_dtype)
+    return int(N.lib().leafk_workspace_bytes(C.byref(cfg), int(B), int(n_frames)))
+
+
 def forward_window(spec: LeafSpec, x_win, T_total: int, t_off: int, n_begin: int, n_count: int,
                    kernel, pool_w, pool_b, alpha, delta, root, ema_w, ema_state=None,
-                   out: Optional[torch.Tensor] = None, want_state: bool = True):
+                   out: Optional[torch.Tensor] = None, want_state: bool = True,
+                   workspace: Optional[torch.Tensor] = None, reuse_banks: bool = False):
     """Frames [n_begin, n_begin+n_count) of clips of length T_total from a sample window
-    (x_win[b,0,i] = sample t_off+i).  Returns (out (B,F,n_count), new ema state (B,F) or None)."""
+    (x_win[b,0,i] = sample t_off+i).  Returns (out (B,F,n_count), new ema state (B,F) or None).
+    ``x_win`` may be a view into a longer buffer (unit stride along samples, any clip stride): no copy is made.
+    ``workspace`` (uint8, at least workspace_bytes(spec, B, n_count)) lets consecutive chunks share one scratch
+    buffer; with ``reuse_banks`` the bank prologue is skipped -- the caller guarantees that the previous call used the
+    same workspace and the same parameters (LEAFK_REUSE_BANKS)."""
     L = N.lib()
-    x_win = _check_input(x_win)
+    if isinstance(x_win, torch.Tensor) and x_win.is_cuda and x_win.dim() == 3 and x_win.shape[1] == 1 \
+            and x_win.shape[0] >= 1 and x_win.shape[2] >= 1 and x_win.dtype in (torch.float32, torch.int16) \
+            and x_win.stride(2) == 1 and (x_win.shape[0] == 1 or x_win.stride(0) >= x_win.shape[2]):
+        ldx = x_win.stride(0) if x_win.shape[0] > 1 else x_win.shape[2]          # strided view: used in place
+    else:
+        x_win = _check_input(x_win)
+        ldx = x_win.shape[2]
     B, _, T_win = x_win.shape
-    cfg = spec.config(x_win.dtype)
+    cfg = spec.config(x_win.dtype, reuse_banks=reuse_banks)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x_win.device)
     with torch.cuda.device(x_win.device):
         if out is None:
@@ -131,10 +147,17 @@ def forward_window(spec: LeafSpec, x_win, T_total: int, t_off: int, n_begin: int
         if ema_state is not None:
             ema_state = _check_param("ema_state", ema_state, B * spec.F, x_win.device)
         ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n_count)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x_win.device)
-        rc = L.leafk_forward_window(C.byref(cfg), C.byref(prm), _ptr(x_win), B, T_win, int(T_total), int(t_off),
+        if workspace is None:
+            if reuse_banks:
+                raise ValueError("reuse_banks needs the workspace of the previous call")
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x_win.device)
+        else:
+            ws = workspace
+            if ws.dtype != torch.uint8 or not ws.is_contiguous() or ws.device != x_win.device or ws.numel() < ws_bytes:
+                raise ValueError(f"workspace must be a contiguous uint8 tensor of >= {ws_bytes} bytes on the input's device")
+        rc = L.leafk_forward_window(C.byref(cfg), C.byref(prm), _ptr(x_win), B, int(ldx), int(T_total), int(t_off),
                                     T_win, int(n_begin), int(n_count), _ptr(ema_state), _ptr(state_out),
-                                    _ptr(out), None, out.stride(0), out.stride(1), _ptr(ws), ws_bytes,
+                                    _ptr(out), None, out.stride(0), out.stride(1), _ptr(ws), ws.numel(),
                                     _stream_ptr(x_win.device))
     N.check(rc, "leafk_forward_window")
     del keep

@@ -34,12 +34,17 @@ def forward_chunked(leaf, x: torch.Tensor, chunk_frames: int = 1000) -> torch.Te
     B, _, T = x.shape
     N = spec.num_frames(T)
     out = torch.empty((B, spec.F, N), dtype=torch.float32, device=x.device)
+    if x.dtype not in (torch.float32, torch.int16) or not x.is_contiguous():
+        x = LF._check_input(x)
+    # one scratch buffer for every chunk: the banks written for the first chunk serve the others (same parameters),
+    # and the chunks read their sample windows in place (views of x, no copies)
+    ws = torch.empty(LF.workspace_bytes(spec, B, min(chunk_frames, N), x.dtype), dtype=torch.uint8, device=x.device)
     state = None
     for n0 in range(0, N, chunk_frames):
         cnt = min(chunk_frames, N - n0)
         lo, hi = needed_samples(spec, T, n0, cnt)
-        win = x[:, :, lo:hi].contiguous()
-        _, state = LF.forward_window(spec, win, T, lo, n0, cnt, *prm, ema_state=state, out=out[:, :, n0:n0 + cnt])
+        _, state = LF.forward_window(spec, x[:, :, lo:hi], T, lo, n0, cnt, *prm, ema_state=state,
+                                     out=out[:, :, n0:n0 + cnt], workspace=ws, reuse_banks=n0 > 0)
     return out
 
 
