@@ -232,3 +232,22 @@ def test_bench_reference_arm_prints_contract_json():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
     assert "workload" in line["config"] and line["vs_baseline"] is None
+
+
+def test_header_constants_match_the_python_binding():
+    """Every #define of include/leafk.h that the ctypes layer mirrors has the same value there, and the Config
+    structure has the fields of leafk_config in the same order."""
+    import re
+    from leaf_pytorch_b200 import _native as N
+    text = open(os.path.join(ROOT, "include", "leafk.h")).read()
+    defs = {m.group(1): int(m.group(2).strip("()")) for m in re.finditer(r"#define\s+(LEAFK_\w+)\s+(\(?-?\d+\)?)", text)}
+    assert defs["LEAFK_ALGO_AUTO"] == N.ALGO_AUTO and defs["LEAFK_ALGO_FP32"] == N.ALGO_FP32 and defs["LEAFK_ALGO_TC"] == N.ALGO_TC
+    assert defs["LEAFK_BWD_2PRODUCT"] == N.BWD_2PRODUCT
+    assert defs["LEAFK_TC_NOPRUNE"] == N.TC_NOPRUNE
+    assert defs["LEAFK_REUSE_BANKS"] == N.REUSE_BANKS
+    assert N.ALGOS["tc_full"] == defs["LEAFK_ALGO_TC"] | defs["LEAFK_TC_NOPRUNE"]
+    flags = [defs["LEAFK_BWD_2PRODUCT"], defs["LEAFK_TC_NOPRUNE"], defs["LEAFK_REUSE_BANKS"]]
+    assert all(f > 15 and f & (f - 1) == 0 for f in flags) and len(set(flags)) == 3     # distinct bits above the kernel choice
+    body = re.search(r"typedef struct leafk_config \{(.*?)\} leafk_config;", text, re.S).group(1)
+    fields = re.findall(r"^\s*(?:int|float)\s+(\w+);", body, re.M)
+    assert fields == [n for n, _ in N.Config._fields_]
