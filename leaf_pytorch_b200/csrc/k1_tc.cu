@@ -14,22 +14,27 @@
 //      D[:, CG:2CG) += xh * Wl       /
 //      D[:, 0:CG)   += xl * Wh          one MMA, N = CG
 // (xl*Wl ~ 2^-22 is dropped.)  The epilogue adds the two column halves: ~2^-21 relative, fp32 class.
+// Forward: per k-step only the channels whose filter is still inside its support run (N = na1 + na3 / na3, two
+// pruning levels, channels in ascending-width order, lo columns mirrored): see k1_tc_layout.cuh and issue_zone below.
 //
 // The A operand is never materialised: see k1_tc_layout.cuh (overlapping-core-matrix descriptor on
 // 8 shifted linear copies of the sample window; row m of phase p = output sample ts + 8m + p).
 //
-// One persistent CTA per SM, 12 warps:
+// One persistent CTA per SM (CTA pairs, tcgen05 cta_group::2), 12 warps:
 //   warps 0-7   epilogue: tcgen05.ld of a finished phase (128 rows x NB columns), hi+lo add, re^2+im^2,
 //               Gaussian window weight by ex2.approx of a per-filter coefficient times (k-centre)^2, FMA
 //               into <= NSLOT frame accumulators per (row, filter) kept in registers for the whole tile;
-//               at the end of the tile a warp-shuffle reduction over rows, a fixed-order sum over the
-//               four row quadrants and one store of the tile's partial pooled sums.
-//   warp  8     allocates tensor memory and issues every MMA (one elected lane, uniform control flow).
-//   warps 9-11  producers: load the fp32 sample window, find its max, scale, split to fp16 hi/lo, and
-//               write the 8 shifted copies; copy p of the next tile is rebuilt as soon as phase p of
-//               the current tile has been consumed (per-phase full/empty mbarriers).
+//               at the end of the tile ONE recursive-halving shuffle reduction over the rows for all (<= 5)
+//               frames at once, a fixed-order sum over the four row quadrants and one store of the tile's
+//               partial pooled sums; a phase later the tile is published to K2 (per-clip counters).
+//   warp  8     allocates tensor memory and issues every MMA (one elected lane, uniform control flow),
+//               zone by zone of constant active channel counts.
+//   warps 9-11  producers: load the sample window into registers, find its max, scale, split to fp16
+//               hi/lo, and write the 8 shifted copies; copy p of the next tile is rebuilt as soon as phase p
+//               of the current tile has been consumed (per-phase full/empty mbarriers).
 // Accumulators rotate through NST = 512/NB tensor-memory stages so the epilogue of phase p overlaps
 // the MMAs of phases p+1.. .  The bank of the CTA's channel group stays resident in shared memory.
+// The kernel is chained to k0 (before) and k2 (after) by programmatic dependent launch.
 #include "leafk_common.cuh"
 #include "k1_tc_layout.cuh"
 #include "tc_ptx.cuh"
