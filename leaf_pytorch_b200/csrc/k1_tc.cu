@@ -839,8 +839,17 @@ bool k1_tc_supported(const Geom& g, const char** why) {
 template <int CG, int NSLOT, int KS>
 static cudaError_t launch_inst_ks(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
                                   int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy, const TcMap& tm) {
-  cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  // the opt-in to > 48 KB of dynamic shared memory is per function and device: raise it only when this launch needs
+  // more than any earlier one asked for (a driver call per forward otherwise)
+  static thread_local int smem_set[64] = {0};
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
   if (err != cudaSuccess) return err;
+  if (dev < 0 || dev >= 64 || smem_set[dev] < smem) {
+    err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    if (dev >= 0 && dev < 64) smem_set[dev] = smem;
+  }
   TcBwdArgs none{nullptr, nullptr, nullptr, 0, 0};
   cudaLaunchConfig_t lc = {};
   lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(tc::NTHREADS); lc.dynamicSmemBytes = (size_t)smem; lc.stream = stream;

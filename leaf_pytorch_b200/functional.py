@@ -58,7 +58,7 @@ def _check_param(name: str, t: Optional[torch.Tensor], numel: int, device) -> Op
         raise TypeError(f"parameter {name} must be float32, got {t.dtype}")
     if t.numel() != numel:
         raise ValueError(f"parameter {name} has {t.numel()} elements, expected {numel}")
-    return t.detach().contiguous()
+    return t if t.is_contiguous() else t.contiguous()     # only the address is used: no detach / new tensor needed
 
 
 def _check_input(x: torch.Tensor) -> torch.Tensor:
