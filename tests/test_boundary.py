@@ -251,3 +251,20 @@ def test_header_constants_match_the_python_binding():
     body = re.search(r"typedef struct leafk_config \{(.*?)\} leafk_config;", text, re.S).group(1)
     fields = re.findall(r"^\s*(?:int|float)\s+(\w+);", body, re.M)
     assert fields == [n for n, _ in N.Config._fields_]
+
+
+def test_host_side_planning_calls_work_without_a_gpu():
+    """Planning entry points of the C ABI are pure host code: workspace size (monotone in clips and frames, covers the
+    per-clip completion counters), kernel coverage, frame count; the config flags reach the C structure."""
+    import torch
+    import leaf_pytorch_b200.functional as LF
+    from leaf_pytorch_b200 import _native as N
+    spec = LF.LeafSpec(F=40, K=401, H=160)
+    w1, w2, w3 = LF.workspace_bytes(spec, 4, 100), LF.workspace_bytes(spec, 256, 100), LF.workspace_bytes(spec, 256, 1000)
+    assert 0 < w1 < w2 < w3
+    assert LF.workspace_bytes(spec, 1 << 16, 100) - LF.workspace_bytes(spec, 1 << 15, 100) >= 4 * (1 << 15)   # counters + partial sums
+    assert LF.tc_supported(40, 401, 160) and LF.tc_supported(80, 401, 160) and LF.tc_supported(8, 1601, 480)
+    assert not LF.tc_supported(40, 401, 40)            # more than 5 frames per 8 samples: CUDA-core kernel
+    assert spec.num_frames(16000) == 100 and spec.num_frames(15999) == 100 and spec.num_frames(16001) == 101
+    cfg = LF.LeafSpec(F=40, K=401, H=160, algo="tc_full", fast_backward=True).config(torch.int16, reuse_banks=True)
+    assert cfg.algo == N.ALGO_TC | N.TC_NOPRUNE | N.BWD_2PRODUCT | N.REUSE_BANKS and cfg.input_format == 1
