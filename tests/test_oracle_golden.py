@@ -88,3 +88,31 @@ def test_c_oracle_matches_reference_golden(name, dbl):
     d = np.abs(out.astype(np.float64) - z["out"])
     assert np.all(d <= 1e-4 * np.abs(z["out"]) + 1e-5), float(d.max())
     assert scaled_err(out, z["out"]) < 2e-5
+
+
+def test_needed_samples_is_exactly_the_dependency_window():
+    """streaming.needed_samples(): frames [n0, n0+cnt) of the pooled energies (no PCEN: no carried history) depend on the
+    samples inside [lo, hi) and on nothing outside -- checked on the oracle by perturbing samples on both sides."""
+    import torch
+    from oracle import leaf_oracle as O
+    import leaf_pytorch_b200.functional as LF
+    from leaf_pytorch_b200.streaming import needed_samples
+    F, K, H, T = 4, 51, 20, 900
+    spec = LF.LeafSpec(F=F, K=K, H=H, compression=False)
+    g = torch.Generator().manual_seed(3)
+    prm = {"kernel": torch.stack([torch.linspace(0.2, 2.5, F), torch.linspace(3.0, 9.0, F)], 1), "pool_w": torch.full((F,), 0.4),
+           "pool_b": torch.zeros(F), "alpha": None, "delta": None, "root": None, "ema_w": None}
+    x = torch.randn(1, 1, T, generator=g, dtype=torch.float64)
+    base = O.forward_f64(x, prm, K, H, compression=False)
+    for n0, cnt in ((0, 3), (7, 5), (spec.num_frames(T) - 4, 4), (20, 1)):
+        lo, hi = needed_samples(spec, T, n0, cnt)
+        y = x.clone()
+        y[..., :lo] += 1.0                                   # everything outside the window changes ...
+        y[..., hi:] -= 1.0
+        out = O.forward_f64(y, prm, K, H, compression=False)
+        assert torch.equal(out[..., n0:n0 + cnt], base[..., n0:n0 + cnt])       # ... and the frames do not
+        for edge in (lo, hi - 1):                            # the window is tight: its first and last sample matter
+            z = x.clone()
+            z[..., edge] += 1.0
+            outz = O.forward_f64(z, prm, K, H, compression=False)
+            assert not torch.equal(outz[..., n0:n0 + cnt], base[..., n0:n0 + cnt])
