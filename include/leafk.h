@@ -30,24 +30,22 @@ extern "C" {
 #define LEAFK_EWORKSPACE (-2) /* workspace too small                                         */
 #define LEAFK_ECUDA (-3)      /* a CUDA runtime call or kernel launch failed                 */
 #define LEAFK_EWINDOW (-4)    /* streaming window does not cover the samples the frames need */
+#define LEAFK_ETIMEOUT (-5)   /* a kernel gave up waiting (stalled host copy); reported by leafk_async_status */
 
 /* Waveform sample type.  With LEAFK_INPUT_S16 every `const float* x` argument points to int16_t samples
  * (same shapes and strides, in elements). */
 #define LEAFK_INPUT_F32 0
 #define LEAFK_INPUT_S16 1
 
+/* Feature element type written by the forward calls (leafk_forward_train always writes float32). */
+#define LEAFK_OUTPUT_F32 0
+#define LEAFK_OUTPUT_BF16 1   /* `out` points to bfloat16 elements, same strides in elements: features for a bf16 backbone
+                                 (the step after the path, reference models/classifier.py:15-17) */
+
 /* Which conv kernel computes the Gabor filterbank stage. */
 #define LEAFK_ALGO_AUTO 0
 #define LEAFK_ALGO_FP32 1     /* direct FP32-FMA correlation (CUDA cores)                    */
 #define LEAFK_ALGO_TC 2       /* tcgen05 Toeplitz GEMM, fp16 hi/lo split (3 products), fp32 accumulate */
-/* Flag OR-ed into `algo`, backward only (opt-in).  The backward correlations then use TWO of the three split
- * products (x_hi*W_hi + x_hi*W_lo): the banks keep full precision, the waveform enters rounded to fp16 (11 bits;
- * the reference's own GPU path rounds both operands to TF32 through cuDNN).  Measured with random
- * upstream gradients (the worst case: the exact gradient is then a random-walk sum, so the relative error stays
- * at the rounding level): 2e-4..9e-4 of max|g|, against 1e-6 for the default three-product backward;
- * 27 % less backward time. */
-#define LEAFK_BWD_2PRODUCT 16
-
 /* Flag OR-ed into `algo`, forward tensor-core kernel only (testing / A-B measurement).  By default the kernel
  * skips, per k-step of 16 taps, the filters whose Gaussian envelope has decayed below exp(-5.5^2/2) = 2.7e-7 of its
  * peak over the whole k-step (|tau| > ceil(5.5 sigma)): the rounding level of the fp16 hi/lo split itself; and beyond
@@ -99,6 +97,7 @@ typedef struct leafk_config {
   int input_format;/* LEAFK_INPUT_F32 (reference layout) or LEAFK_INPUT_S16: 16-bit PCM, converted
                       in the kernel as s/32768 (what soundfile hands the reference's data pipeline,
                       utilities/data/utils.py:136-157); halves the HBM / PCIe bytes of the waveform */
+  int output_format;/* LEAFK_OUTPUT_F32 (reference) or LEAFK_OUTPUT_BF16 */
 } leafk_config;
 
 int leafk_version(void);
@@ -137,11 +136,40 @@ int leafk_forward_window(const leafk_config* cfg, const leafk_params* prm, const
 
 /* Parameter gradients of sum(out * grad_out): replaces autograd through frontend.py:78-89
  * (train.py:258).  x (B,1,T), grad_out (B,F,N), saved_p (B,F,N) from leafk_forward.  Gradients
- * are written (not accumulated).  grad_x: optional (B,1,T) or NULL (train.py never needs it). */
+ * are written (not accumulated).  grad_x: optional (B,1,T) gradient w.r.t. the float32 waveform, or NULL
+ * (train.py never needs it).  Works for every geometry: where the tensor-core training kernel applies it re-runs
+ * leafk_forward_train into the workspace (prefer leafk_forward_train + leafk_backward_saved there: one pass less),
+ * elsewhere a generic FP32 kernel computes the correlations. */
 int leafk_backward(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
                    const float* grad_out, const float* saved_p, const leafk_grads* grads,
                    float* grad_x, void* workspace, size_t workspace_bytes, void* stream);
 size_t leafk_backward_workspace_bytes(const leafk_config* cfg, int B, int T);
+
+/* ---- training (reference train.py:233-265: forward, loss.backward()) -------------------------------------------
+ * On geometries the tensor-core training kernel covers (leafk_train_supported) the forward that precedes a backward
+ * is leafk_forward_train: besides the features it saves, per (clip, filter, frame), the floored pooled energy p and
+ * three pooled bilinear forms Q_mu, Q_sigma, Q_poolw of the correlations with the derivative banks.  With those the
+ * backward needs no correlation at all:  dL/dmu = 2 sum dp Q_mu,  dL/dsigma = 2 sum dp Q_sigma,
+ * dL/ds = sum dp Q_poolw / (s^3 c^2)  (dp = gradient w.r.t. p).  Forward + backward cost three Gabor
+ * correlations instead of one + three.
+ *   saved  (4,B,F,N) float32: [0] = p, [1..3] = Q_mu, Q_sigma, Q_poolw
+ * leafk_backward_saved: gradients are written (not accumulated).  x and grad_x (B,1,T) may both be NULL; when grad_x
+ * is given (float32 waveforms only) x is needed and a generic FP32 pass adds dL/dx.
+ * Any other geometry: leafk_forward (saved_p) + leafk_backward, which runs the generic FP32 backward. */
+int leafk_train_supported(int F, int K, int H);
+size_t leafk_train_workspace_bytes(const leafk_config* cfg, int B, int T);
+int leafk_forward_train(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T, float* out,
+                        float* saved, void* workspace, size_t workspace_bytes, void* stream);
+size_t leafk_backward_saved_workspace_bytes(const leafk_config* cfg, int B, int T, int want_grad_x);
+int leafk_backward_saved(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
+                         const float* grad_out, const float* saved, const leafk_grads* grads, float* grad_x,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Asynchronous error word of the LAST forward that used `workspace` (its first 4 bytes).  The
+ * kernels never trap on a wait that depends on the host: a slice-ready flag that does not arrive within ~10 s
+ * (stalled or failed H2D copy) makes the forward finish on whatever data is there and record the condition; this
+ * call (a synchronous 4-byte read -- call it after synchronising the stream) returns LEAFK_ETIMEOUT then. */
+int leafk_async_status(const void* workspace);
 
 /* End-to-end call on HOST buffers: x_host (B,1,T) and out_host (B,F,N) are host pointers
  * (pinned for full speed).  The H2D copy is enqueued on copy_stream in `n_slices` (<= 32) pieces,

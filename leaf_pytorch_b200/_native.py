@@ -17,7 +17,6 @@ LIB_PATH = os.environ.get("LEAFK_LIB") or os.path.join(os.path.dirname(os.path.a
 ALGO_AUTO, ALGO_FP32, ALGO_TC = 0, 1, 2
 TC_NOPRUNE = 32        # LEAFK_TC_NOPRUNE: every filter over all taps (no support pruning of the k-steps)
 ALGOS = {"auto": ALGO_AUTO, "fp32": ALGO_FP32, "tc": ALGO_TC, "tc_full": ALGO_TC | TC_NOPRUNE}
-BWD_2PRODUCT = 16
 REUSE_BANKS = 64       # LEAFK_REUSE_BANKS: the workspace still holds the banks of the same parameters (chunked clips)
 
 SYMBOLS = (
@@ -25,6 +24,8 @@ SYMBOLS = (
     "leafk_workspace_bytes", "leafk_forward", "leafk_forward_window", "leafk_backward",
     "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end", "leafk_profile_k1_clock", "leafk_profile_tc_schedule",
     "leafk_forward_host_async", "leafk_event_create", "leafk_event_destroy", "leafk_event_synchronize",
+    "leafk_train_supported", "leafk_train_workspace_bytes", "leafk_forward_train", "leafk_backward_saved",
+    "leafk_backward_saved_workspace_bytes", "leafk_async_status",
 )
 
 
@@ -42,7 +43,8 @@ class Grads(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("F", C.c_int), ("K", C.c_int), ("H", C.c_int), ("pcen_floor", C.c_float),
-                ("clamp_min", C.c_float), ("compression", C.c_int), ("algo", C.c_int), ("input_format", C.c_int)]
+                ("clamp_min", C.c_float), ("compression", C.c_int), ("algo", C.c_int), ("input_format", C.c_int),
+                ("output_format", C.c_int)]
 
 
 _lib = None
@@ -104,6 +106,19 @@ def lib() -> C.CDLL:
         L.leafk_event_destroy.argtypes = [vp]
         L.leafk_event_synchronize.restype = i
         L.leafk_event_synchronize.argtypes = [vp]
+        L.leafk_train_supported.restype = i
+        L.leafk_train_supported.argtypes = [i, i, i]
+        L.leafk_train_workspace_bytes.restype = sz
+        L.leafk_train_workspace_bytes.argtypes = [C.POINTER(Config), i, i]
+        L.leafk_forward_train.restype = i
+        L.leafk_forward_train.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, vp, vp, sz, vp]
+        L.leafk_backward_saved_workspace_bytes.restype = sz
+        L.leafk_backward_saved_workspace_bytes.argtypes = [C.POINTER(Config), i, i, i]
+        L.leafk_backward_saved.restype = i
+        L.leafk_backward_saved.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, vp, C.POINTER(Grads),
+                                           vp, vp, sz, vp]
+        L.leafk_async_status.restype = i
+        L.leafk_async_status.argtypes = [vp]
         L.leafk_launch_count.restype = ll
         L.leafk_launch_count.argtypes = [i]
         _lib = L

@@ -68,7 +68,14 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
   int my_pos = 0;
   if (w16 != nullptr) {
     for (int i = threadIdx.x; i < Fp; i += blockDim.x)
-      sm_key[i] = (i < F) ? fminf(fmaxf(kernel[2 * i + 1], bc.sigma_lo), bc.sigma_hi) : -1.0f;
+    {
+      float key = -1.0f;                                     // padding filter
+      if (i < F) {
+        const float raw = kernel[2 * i + 1];
+        key = (raw != raw) ? bc.sigma_hi : fminf(fmaxf(raw, bc.sigma_lo), bc.sigma_hi);   // NaN: widest (never pruned)
+      }
+      sm_key[i] = key;
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < Fp; i += blockDim.x) {
       const float ki = sm_key[i];
@@ -163,11 +170,11 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
     }
     return;
   }
-  const float mu = fminf(fmaxf(kernel[2 * f], 0.f), bc.mu_hi);
-  const float sg = fminf(fmaxf(kernel[2 * f + 1], bc.sigma_lo), bc.sigma_hi);
+  const float mu = clamp_nan(kernel[2 * f], 0.f, bc.mu_hi);
+  const float sg = clamp_nan(kernel[2 * f + 1], bc.sigma_lo, bc.sigma_hi);
   const float norm = 1.0f / (bc.sqrt_2pi * sg);
   const float inv2s2 = 1.0f / (2.0f * (sg * sg));
-  const float ps = fminf(fmaxf(pool_w[f], bc.pool_lo), 0.5f);
+  const float ps = clamp_nan(pool_w[f], bc.pool_lo, 0.5f);
   const float den = (ps * 0.5f) * (float)(K - 1);
   const float centre = (float)(0.5 * (double)(K - 1));
 
@@ -214,41 +221,43 @@ k0_banks_kernel(const float* __restrict__ kernel, const float* __restrict__ pool
 }
 
 // ---------------------------------------------------------------------------------------------
-// Backward banks.  For every filter three complex banks in the tcgen05 layout (fp16 hi/lo, own
-// power-of-two scale each):  h (kind 0),  tau*h (kind 1, d/dmu up to the factor i),
-// (tau^2/sigma^3 - 1/sigma)*h (kind 2, d/dsigma).  Group layout: see tc::bwd_channel().
-// bprm[f] = {pool exp2 coefficient, shift_y, shift_z, shift_v, sigma, pool_s, 0, 0}.
+// Training banks.  For every filter three complex banks in the tcgen05 TRAINING layout (k1_tc_layout.cuh; fp16
+// hi/lo, own power-of-two scale each):  h (kind 0),  tau*h (kind 1, d/dmu up to the factor i),
+// (tau^2/sigma^3 - 1/sigma)*h (kind 2, d/dsigma).  Channel order: tc::train_channel().
+// tprm[f] = {pool exp2 coefficient, shift_y, shift_z, shift_v, sigma, pool_s, 0, 0}.
 __global__ void __launch_bounds__(128)
-k0_banks_bwd_kernel(const float* __restrict__ kernel, const float* __restrict__ pool_w, BankConsts bc, int F,
-                    int K, int Kp, int FB, float* __restrict__ bprm, uint8_t* __restrict__ w16b) {
+k0_banks_train_kernel(const float* __restrict__ kernel, const float* __restrict__ pool_w, BankConsts bc, int F,
+                      int K, int Kp, int FB, float* __restrict__ tprm, uint8_t* __restrict__ w16t, int* done, int n_done) {
   __shared__ float smax[3][4];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // K1 waits for this grid's completion itself
   const int f = blockIdx.x;                          // padded filter index (f >= F: zero banks)
   const int CG = 6 * FB;
   const int grp = f / FB, fl = f % FB;
-  uint8_t* gb = w16b + (size_t)grp * tc::b_group_bytes(CG, Kp);
+  uint8_t* gb = w16t + (size_t)grp * tc::t_group_bytes(CG, Kp);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (done != nullptr)
+    for (int i = blockIdx.x * blockDim.x + tid; i < n_done; i += gridDim.x * blockDim.x) done[i] = 0;
   if (f >= F) {
     for (int k = tid; k < Kp; k += blockDim.x)
       for (int kind = 0; kind < 3; ++kind)
         for (int ri = 0; ri < 2; ++ri) {
-          const int c = tc::bwd_channel(FB, fl, kind, ri);
+          const int c = tc::train_channel(FB, fl, kind, ri);
           const __half z = __float2half_rn(0.f);
-          *reinterpret_cast<__half*>(gb + tc::g_hi_main(CG, Kp, c, k)) = z;
-          *reinterpret_cast<__half*>(gb + tc::g_lo_main(CG, Kp, c, k)) = z;
-          *reinterpret_cast<__half*>(gb + tc::g_hi_corr(CG, Kp, c, k)) = z;
+          *reinterpret_cast<__half*>(gb + tc::t_hi(CG, Kp, c, k)) = z;
+          *reinterpret_cast<__half*>(gb + tc::t_lo(CG, Kp, c, k)) = z;
         }
     if (tid == 0) {
-      float* bp = bprm + (size_t)f * 8;
+      float* bp = tprm + (size_t)f * 8;
       bp[0] = -1.0f;
       for (int i = 1; i < 8; ++i) bp[i] = 0.f;
     }
     return;
   }
-  const float mu = fminf(fmaxf(kernel[2 * f], 0.f), bc.mu_hi);
-  const float sg = fminf(fmaxf(kernel[2 * f + 1], bc.sigma_lo), bc.sigma_hi);
+  const float mu = clamp_nan(kernel[2 * f], 0.f, bc.mu_hi);
+  const float sg = clamp_nan(kernel[2 * f + 1], bc.sigma_lo, bc.sigma_hi);
   const float norm = 1.0f / (bc.sqrt_2pi * sg);
   const float inv2s2 = 1.0f / (2.0f * (sg * sg));
-  const float ps = fminf(fmaxf(pool_w[f], bc.pool_lo), 0.5f);
+  const float ps = clamp_nan(pool_w[f], bc.pool_lo, 0.5f);
   const float den = (ps * 0.5f) * (float)(K - 1);
   const float inv_s3 = 1.0f / (sg * sg * sg), inv_s = 1.0f / sg;
 
@@ -273,11 +282,11 @@ k0_banks_bwd_kernel(const float* __restrict__ kernel, const float* __restrict__ 
   for (int q = 0; q < 3; ++q) {
     const float m = fmaxf(fmaxf(smax[q][0], smax[q][1]), fmaxf(smax[q][2], smax[q][3]));
     int ex = 0;
-    if (m > 0.f) (void)frexpf(m, &ex);
-    shift[q] = (m > 0.f) ? 14 - ex : 0;
+    if (m > 0.f && m < 3.0e38f) (void)frexpf(m, &ex);
+    shift[q] = (m > 0.f && m < 3.0e38f) ? 14 - ex : 0;
   }
   if (tid == 0) {
-    float* bp = bprm + (size_t)f * 8;
+    float* bp = tprm + (size_t)f * 8;
     bp[0] = (float)(-0.5 * 1.4426950408889634 / ((double)den * (double)den));
     bp[1] = (float)shift[0]; bp[2] = (float)shift[1]; bp[3] = (float)shift[2];
     bp[4] = sg; bp[5] = ps; bp[6] = 0.f; bp[7] = 0.f;
@@ -303,10 +312,9 @@ k0_banks_bwd_kernel(const float* __restrict__ kernel, const float* __restrict__ 
         const float sc = ldexpf(v[kind][ri], shift[kind]);
         const __half hi = __float2half_rn(sc);
         const __half lo = __float2half_rn(sc - __half2float(hi));
-        const int c = tc::bwd_channel(FB, fl, kind, ri);
-        *reinterpret_cast<__half*>(gb + tc::g_hi_main(CG, Kp, c, k)) = hi;
-        *reinterpret_cast<__half*>(gb + tc::g_lo_main(CG, Kp, c, k)) = lo;
-        *reinterpret_cast<__half*>(gb + tc::g_hi_corr(CG, Kp, c, k)) = hi;
+        const int c = tc::train_channel(FB, fl, kind, ri);
+        *reinterpret_cast<__half*>(gb + tc::t_hi(CG, Kp, c, k)) = hi;
+        *reinterpret_cast<__half*>(gb + tc::t_lo(CG, Kp, c, k)) = lo;
       }
   }
 }
@@ -327,9 +335,10 @@ void bank_bounds(int K, float* mu_hi, float* sigma_lo, float* sigma_hi, float* p
   *mu_hi = bc.mu_hi; *sigma_lo = bc.sigma_lo; *sigma_hi = bc.sigma_hi; *pool_lo = bc.pool_lo;
 }
 
-void launch_k0_bwd(const float* kernel, const float* pool_w, int F, int K, int Kp, int FB, int n_groups,
-                   float* bprm, uint8_t* w16b, cudaStream_t stream) {
-  k0_banks_bwd_kernel<<<n_groups * FB, 128, 0, stream>>>(kernel, pool_w, make_consts(K), F, K, Kp, FB, bprm, w16b);
+void launch_k0_train(const float* kernel, const float* pool_w, int F, int K, int Kp, int FB, int n_groups,
+                     float* tprm, uint8_t* w16t, int* done, int n_done, cudaStream_t stream) {
+  k0_banks_train_kernel<<<n_groups * FB, 128, 0, stream>>>(kernel, pool_w, make_consts(K), F, K, Kp, FB, tprm, w16t,
+                                                         done, n_done);
 }
 
 void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,

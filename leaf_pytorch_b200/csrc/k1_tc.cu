@@ -35,6 +35,18 @@
 // Accumulators rotate through NST = 512/NB tensor-memory stages so the epilogue of phase p overlaps
 // the MMAs of phases p+1.. .  The bank of the CTA's channel group stays resident in shared memory.
 // The kernel is chained to k0 (before) and k2 (after) by programmatic dependent launch.
+// Registers: the CTA launches with 168 per thread; warps 8-11 (MMA issuer + producers) give theirs back
+// (setmaxnreg.dec) and the two epilogue warpgroups take them (setmaxnreg.inc), so the accumulator-heavy epilogues
+// do not spill.
+//
+// MODE 1 = TRAINING forward (Leaf.forward when parameters require grad).  Besides y it runs the two derivative
+// banks z = x*(tau h), v = x*((tau^2/sigma^3 - 1/sigma) h) ("equivalent without forming dW") and pools,
+// with the SAME Gaussian windows as the energy, the three bilinear forms the parameter gradients need:
+//      Q_mu[n]    = sum_t g[k] (y_im z_re - y_re z_im)       dL/dmu    = 2 sum_n dp[n] Q_mu[n]
+//      Q_sigma[n] = sum_t g[k] (y_re v_re + y_im v_im)       dL/dsigma = 2 sum_n dp[n] Q_sigma[n]
+//      Q_pw[n]    = sum_t g[k] (k - c)^2 e[t]                dL/ds     = sum_n dp[n] Q_pw[n] / (s^3 c^2)
+// because sum_t de[t] q[t] with de[t] = sum_n dp[n] g[t - t_n] is sum_n dp[n] (pooled q)[n].  The backward pass then
+// needs no correlation at all (bwd.cu): forward + backward cost 3 correlations instead of 1 + 3.
 #include "leafk_common.cuh"
 #include "k1_tc_layout.cuh"
 #include "tc_ptx.cuh"
@@ -43,11 +55,6 @@
 #include <cstdio>
 #include <cstring>
 
-#ifndef LEAFK_EXP
-#define LEAFK_EXP 0      // timing experiments only (results wrong): 1 = no epilogue loads + arithmetic, 2 = producers skip the
-                         // copies, 4 = epilogue loads only, 8 = epilogue arithmetic only,
-                         // 16 = no epilogue work on the MMA warp's scheduler (quadrant 0), 32 = only there
-#endif
 
 namespace leafk {
 
@@ -67,6 +74,8 @@ struct Misc {                 // small shared state behind the big regions
   uint64_t a_empty[NPHASE];
   uint64_t acc_full[4];
   uint64_t acc_empty[4];
+  uint64_t bank_full;         // this CTA's bank has landed (bulk copy, complete_tx)
+  uint64_t bank_pair;         // rank 0: both CTAs' banks have landed
   uint32_t tmem_base;
   int sx_ring[4];
   float red[4];
@@ -91,7 +100,7 @@ __device__ __forceinline__ void build_copy_regs(tc::Misc* misc, const uint32_t (
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int jj = ptid + c * tc::PROD_THREADS;
-    if (jj < (((LEAFK_EXP & 2) != 0) ? 0 : nchunk)) {
+    if (jj < nchunk) {
       uint4 oh, ol;
       if ((P & 1) == 0) {
         oh = make_uint4(wh[c][s], wh[c][s + 1], wh[c][s + 2], wh[c][s + 3]);
@@ -111,20 +120,21 @@ __device__ __forceinline__ void build_copy_regs(tc::Misc* misc, const uint32_t (
   if (lane == 0) mbar_arrive_rank0(&misc->a_full[P]);      // the MMA issuer lives in rank 0 of the pair
 }
 
-// Extra arguments of the backward variant (MODE 1): the epilogue turns the three correlations
-// y, z = x*(tau h), v = x*((tau^2/sigma^3 - 1/sigma) h) into the per-filter sums that give the gradients of
-// centre, width and pooling width ("equivalent without forming dW").
 // Optional host-pipelining hook: when `ready` is non-null the producers wait, before touching clip b, until
 // ready[b / clips_per_flag] != 0.  The flags are set by stream-ordered 32-bit writes that follow each slice of
 // the H2D copy on another stream, so ONE persistent launch overlaps the whole PCIe transfer (leafk_forward_host).
+// A flag that does not arrive within ~10 s (copy stalled, stream torn down) does not kill the context: the producer
+// records LEAFK_ASYNC_H2D_TIMEOUT in *err, goes on with whatever is in the buffer, and the host API reports the
+// error word after its next synchronisation (leafk_async_status).
 struct TcReady {
   const int* ready;
   int clips_per_flag;
   long long* perf;      // optional: CTA 0 stores {SM cycles, nanoseconds} of its lifetime (effective SM clock)
+  int* err;             // asynchronous error word in the workspace (0 = none), may be null
 };
 
-// Forward only: the width-sorted channel order and the per-k-step active channel counts written by k0
-// (k1_tc_layout.cuh, "SUPPORT PRUNING").
+// Forward: the width-sorted channel order and the per-k-step active channel counts written by k0
+// (k1_tc_layout.cuh, "SUPPORT PRUNING").  Both modes: the per-clip completion counters read by K2.
 struct TcMap {
   int* done;            // [B] per-clip completion counters for K2 (one increment per epilogue warp and stored tile)
   const int* perm;      // [n_groups * CG/2] sorted position -> filter index (>= F: padding)
@@ -132,13 +142,10 @@ struct TcMap {
                         // running; ints [16,32) {na3 of level L's rising zone, of its falling zone}
 };
 
-struct TcBwdArgs {
-  const float* dpT;     // (B, N, F) gradient w.r.t. the floored pooled energies, frame-major
-  const float* bprm;    // (Fpad, 8): [0] pooling exp2 coefficient, [1..3] power-of-two shifts of the y,z,v banks
-  float* bpart;         // (ctas_per_group, Fpad, 4) per-CTA partial sums: {S_mu, S_sigma, S_poolw, 0}
+// Training forward (MODE 1): per-filter constants written by k0_banks_train_kernel.
+struct TcTrainArgs {
+  const float* tprm;    // (Fpad, 8): [0] pooling exp2 coefficient, [1..3] power-of-two shifts of the y,z,v banks
   int Fpad;             // n_groups * FB
-  int skip_xlo;         // 1: drop the x_lo*W_hi product (2-product mode): the waveform enters with fp16 rounding
-                        //    (zero-mean, averages out over the B*T terms of a gradient), the banks keep hi+lo
 };
 
 // ---- pruned MMA issue (forward) ------------------------------------------------------------------------------
@@ -242,6 +249,7 @@ __device__ __forceinline__ void producer_loop(const Geom& g, const float* __rest
   using namespace tc;
   const int ptid = tid - PROD_WARP0 * 32;
   const int nchunk = sp.CL / 8;            // 16-byte chunks per copy
+  bool gave_up = false;                    // a ready flag timed out: stop waiting for the others too
   int it = 0;
   for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
     const long long u = 2 * pu + rank;
@@ -249,14 +257,22 @@ __device__ __forceinline__ void producer_loop(const Geom& g, const float* __rest
     const int b = valid ? (int)(u / g.n_tiles) : 0, tile = valid ? (int)(u % g.n_tiles) : 0;
     const long long ts = g.te_lo + (long long)tile * TILE;
     const size_t xrow = (size_t)b * g.ldx;
-    if (valid && rdy.ready != nullptr && ptid == 0) {       // clip b still in flight over PCIe?
+    if (valid && rdy.ready != nullptr && ptid == 0 && !gave_up) {       // clip b still in flight over PCIe?
       const int* flag = rdy.ready + b / rdy.clips_per_flag;
       int v;
-      unsigned spins = 0;
-      do {
-        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (v == 0) { __nanosleep(200); if (++spins > (1u << 24)) __trap(); }
-      } while (v == 0);
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if (v == 0) {
+        const long long t0 = global_timer_ns();
+        do {
+          __nanosleep(200);
+          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          if (v == 0 && global_timer_ns() - t0 > H2D_TIMEOUT_NS) {      // stalled copy: report, do not trap
+            if (rdy.err != nullptr) atomicExch(rdy.err, LEAFK_ASYNC_H2D_TIMEOUT);
+            gave_up = true;
+            break;
+          }
+        } while (v == 0);
+      }
     }
     named_bar_sync(BAR_PROD, PROD_THREADS);        // clip b resident; max scratch of the previous tile consumed
     // this thread's samples: 16 per chunk (staged index 8 jj .. 8 jj + 15, sample ts - padL + index)
@@ -313,20 +329,109 @@ __device__ __forceinline__ void producer_loop(const Geom& g, const float* __rest
   }
 }
 
-// KS > 0: number of k-steps known at compile time (26 for the default 401-tap window): the MMA issue loop is
+
+// ---- tile end, part 1: row sums over the 32 rows of a warp ----------------------------------------------------
+// acc[vi][j]: this row's partial pooled sums of NV "virtual filters" (forward: CG/4 filters; training: FB/2 filters
+// x 4 pooled quantities) for its NSLOT frame slots (frames nb .. nb+NSLOT-1).  Writes the warp's sums to
+// pw[slot * NV + vi], slot = frame - n_first.
+// This section is on the critical path: while the epilogue warps are in it nobody drains the accumulator stages.
+// The shared-memory pipe is ~86 % busy with tensor-core operand fetches, so every dependent trip through it (shuffle
+// level, store/load pair) costs 150-350 cycles: the row sums therefore run as ONE recursive-halving reduction over
+// all (<= 5) frames at once -- 5 dependent shuffle levels per tile instead of 5 per frame or per (frame, filter).
+template <int NV, int NSLOT>
+__device__ __forceinline__ void tile_end_rowsums(const float (&acc)[NV][NSLOT], float* pw, float* red, int lane, int nb,
+                                                 int n_first, int n_last, int SL) {
+  for (int i = lane; i < SL * NV; i += 32) pw[i] = 0.f;
+  __syncwarp();
+  const int nb_lo = __shfl_sync(0xffffffffu, nb, 0);
+  int nb_hi = __shfl_sync(0xffffffffu, nb, 31) + NSLOT - 1;
+  constexpr int NFR = NSLOT + 2;                        // frames the fast path covers
+  if (NSLOT == 3 && nb_hi - nb_lo < NFR) {
+    if (nb_hi > n_last) nb_hi = n_last;
+    const int red_vi = halving_index<NV, 16>(lane);     // virtual filter whose row sum the reduction leaves in this lane
+    const int eo = nb - nb_lo;                          // 0..2: this lane's first frame relative to the warp's
+    constexpr int H1 = (NV + 1) / 2;
+    const bool up = (lane & 16) != 0;
+    float k1[NFR][H1];
+#pragma unroll
+    for (int d = 0; d < NFR; ++d) {
+#pragma unroll
+      for (int i = 0; i < H1; ++i) {
+        float lo_v = 0.f, hi_v = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < NSLOT; ++jj) {
+          if (d - jj >= 0 && d - jj <= 2) {             // frame d is slot jj of the lanes with eo == d - jj
+            lo_v = (eo == d - jj) ? acc[i][jj] : lo_v;
+            if (i + H1 < NV) hi_v = (eo == d - jj) ? acc[i + H1 < NV ? i + H1 : 0][jj] : hi_v;
+          }
+        }
+        k1[d][i] = (up ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, up ? lo_v : hi_v, 16);
+      }
+    }
+    float tot[NFR];
+    halving_multi<NFR, H1, 8>(k1, lane, tot);
+#pragma unroll
+    for (int d = 0; d < NFR; ++d) {
+      const int slot = nb_lo + d - n_first;
+      if (red_vi >= 0 && nb_lo + d <= nb_hi && slot < SL) pw[slot * NV + red_vi] = tot[d];
+    }
+  } else {
+    // generic geometry (more frames per warp): row sums through the transpose buffer, one frame at a time
+    if (nb_hi > n_last) nb_hi = n_last;
+    for (int n = nb_lo; n <= nb_hi; ++n) {
+      const int slot = n - n_first;
+      if (slot >= SL) break;
+      const int j = n - nb;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float v = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < NSLOT; ++jj) v = (j == jj) ? acc[i][jj] : v;
+        red[i * 33 + lane] = v;
+      }
+      __syncwarp();
+      for (int vi = lane; vi < NV; vi += 32) {
+        const float* rr = red + vi * 33;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int r = 0; r < 32; r += 4) { s0 += rr[r]; s1 += rr[r + 1]; s2 += rr[r + 2]; s3 += rr[r + 3]; }
+        pw[slot * NV + vi] = (s0 + s1) + (s2 + s3);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ---- tile end, part 2: fixed-order sum over the four row quadrants, undo the power-of-two scaling, store ------
+// s_out[idx] = {offset of quadrant 0's sum in the reduction buffer, offset in the tile's partial-sum block or -1,
+// bank exponent, 0}; the stored value is sum * 2^-(2 sx + exponent).
+__device__ __forceinline__ void tile_end_store(const float* pw_buf, const int4* s_out, int n_entries, int etid,
+                                               bool valid, float* dst, int sx, int qstride) {
+  for (int idx = etid; idx < n_entries; idx += tc::EPI_WARPS * 32) {
+    const int4 o = s_out[idx];
+    if (valid && o.y >= 0) {
+      const float* src = pw_buf + o.x;
+      float s = 0.f;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) s += src[(size_t)qq * qstride];
+      dst[o.y] = scalbnf(s, -(2 * sx + o.z));
+    }
+  }
+}
+
+// KS > 0: number of k-steps known at compile time (26 for the default 401-tap window): the training MMA issue loop is
 // fully unrolled with immediate descriptor offsets -- with a runtime trip count the per-iteration descriptor
 // arithmetic made the single issuing lane the bottleneck (149 cycles per k-step measured vs 124 issued tight).
+// BIGP: producers keep 3-4 chunks per thread (windows longer than ~520 taps) and need more registers.
 template <int CG, int NSLOT, int MODE, int KS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NTHREADS, 1)
 k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restrict__ w16,
-             const float* __restrict__ cprm, float* __restrict__ ppart, int n_groups, const TcBwdArgs ba,
+             const float* __restrict__ cprm, float* __restrict__ ppart, int n_groups, const TcTrainArgs ta,
              const TcReady rdy, const TcMap tm) {
   using namespace tc;
-  constexpr int NB = 2 * CG;                 // accumulator columns per stage (hi | lo products)
+  constexpr int NB = (MODE == 0) ? 2 * CG : CG;   // accumulator columns per stage (forward: hi | lo products)
   constexpr int NST = (512 / NB) > 4 ? 4 : (512 / NB);
-  constexpr int FPT = CG / 4;                // filters per epilogue thread
-  constexpr uint32_t IDESC_MAIN = idesc_f16(256, NB);   // M = 256: 128 rows from each CTA of the pair
-  constexpr uint32_t IDESC_CORR = idesc_f16(256, CG);
+  constexpr int NV = virt_per_thread(CG, MODE);   // virtual filters per epilogue thread
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const SmemPlan sp = smem_plan(CG, g.Kp, g.SL, MODE, NSLOT);
@@ -341,7 +446,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   long long perf_c0 = 0, perf_t0 = 0;
   if (rdy.perf != nullptr && blockIdx.x == 0 && tid == 0) {
     perf_c0 = clock64();
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(perf_t0));
+    perf_t0 = global_timer_ns();
   }
   // CTA pair = cluster of 2 (same TPC).  Both CTAs serve the same channel group; the pair takes two units
   // (tiles) per iteration, rank r the unit 2*pair_unit + r.  Rank 0 issues the MMAs for both.
@@ -352,166 +457,184 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   const int pairs_in_grp = (n_pairs - grp + n_groups - 1) / n_groups;
   const long long n_units = (long long)g.B * g.n_tiles;
   const long long n_pair_units = (n_units + 1) / 2;
-  const int cta_in_grp = pair_in_grp * 2 + (int)rank;    // row of the backward partial buffer
   const int ksteps = g.Kp / KSTEP;
+  const int cpt = (sp.CL / 8 + PROD_THREADS - 1) / PROD_THREADS;     // 16-byte chunks of a copy per producer thread
 
   // ---- one-time setup ---------------------------------------------------------------------------
-  // Programmatic dependent launch (forward): this grid may have been scheduled while the bank prologue k0 was still
-  // running -- wait for its completion before reading anything it wrote; and let the PCEN kernel be scheduled as soon
-  // as SMs free up at the tail of this grid (it waits for our completion itself).
-  if constexpr (MODE == 0) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  }
-  {
-    // this CTA's bank regions: R1 (main MMA) then R2 (corr MMA), from the group's global image
-    const uint8_t* gimg = w16 + (size_t)grp * b_group_bytes(CG, g.Kp);
-    const size_t r1 = r1_bytes(CG, g.Kp), r2 = r2_bytes(CG, g.Kp);
-    const uint4* src1 = reinterpret_cast<const uint4*>(gimg + rank * r1);
-    const uint4* src2 = reinterpret_cast<const uint4*>(gimg + 2 * r1 + rank * r2);
-    uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = tid; i < (int)(r1 / 16); i += NTHREADS) dst[i] = __ldg(src1 + i);
-    for (int i = tid; i < (int)(r2 / 16); i += NTHREADS) dst[r1 / 16 + i] = __ldg(src2 + i);
-  }
   if (tid == 0) {
-    // a_full / acc_empty live on rank 0 and collect arrivals from BOTH CTAs; a_empty / acc_full are local
+    // a_full / acc_empty / bank_pair live on rank 0 and collect arrivals from BOTH CTAs; a_empty / acc_full are local
     // and are signalled in both CTAs by the multicast tcgen05.commit of rank 0.
     for (int p = 0; p < NPHASE; ++p) { mbar_init(&misc->a_full[p], 2 * PROD_WARPS); mbar_init(&misc->a_empty[p], 1); }
     for (int s = 0; s < 4; ++s) { mbar_init(&misc->acc_full[s], 1); mbar_init(&misc->acc_empty[s], 2 * EPI_WARPS); }
+    mbar_init(&misc->bank_full, 1);
+    mbar_init(&misc->bank_pair, 2);
     mbar_init_fence();
   }
   if (warp == MMA_WARP) tmem_alloc_pair<512>(&misc->tmem_base);
-  fence_proxy_async_smem();                  // bank written with generic stores, read by the MMA (async proxy)
   tc_fence_before();
   cluster_sync_all();                        // barriers + TMEM of both CTAs ready before any remote arrive / MMA
   tc_fence_after();
   const uint32_t tmem = misc->tmem_base;
+  // Programmatic dependent launch: this grid may have been scheduled while the bank prologue k0 was still running --
+  // wait for its completion before reading anything it wrote; and let the PCEN kernel be scheduled as soon as SMs
+  // free up at the tail of this grid (it waits for our completion itself).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp >= PROD_WARP0) {
-    // =========================================== PRODUCERS ======================================
-    const int cpt = (sp.CL / 8 + PROD_THREADS - 1) / PROD_THREADS;     // 16-byte chunks of a copy per producer thread
-    if (cpt <= 2)
-      producer_loop<2>(g, x, rdy, sp, misc, s_acopy, tid, lane, warp, rank, pair_in_grp, pairs_in_grp, n_units, n_pair_units);
-    else if (cpt == 3)
-      producer_loop<3>(g, x, rdy, sp, misc, s_acopy, tid, lane, warp, rank, pair_in_grp, pairs_in_grp, n_units, n_pair_units);
-    else
-      producer_loop<4>(g, x, rdy, sp, misc, s_acopy, tid, lane, warp, rank, pair_in_grp, pairs_in_grp, n_units, n_pair_units);
-  } else if (warp == MMA_WARP) {
-    // =========================================== MMA ISSUER (rank 0 only) =======================
-    if (rank == 0) {
+  if (warp >= MMA_WARP) {
+    // ---- warpgroup 2: MMA issuer (warp 8) + producers (warps 9-11): give registers to the epilogue warpgroups
+    if (cpt <= 2) setmaxnreg_dec<104>(); else setmaxnreg_dec<152>();
+    if (warp >= PROD_WARP0) {
+      // =========================================== PRODUCERS ======================================
+      if (cpt <= 2)
+        producer_loop<2>(g, x, rdy, sp, misc, s_acopy, tid, lane, warp, rank, pair_in_grp, pairs_in_grp, n_units, n_pair_units);
+      else if (cpt == 3)
+        producer_loop<3>(g, x, rdy, sp, misc, s_acopy, tid, lane, warp, rank, pair_in_grp, pairs_in_grp, n_units, n_pair_units);
+      else
+        producer_loop<4>(g, x, rdy, sp, misc, s_acopy, tid, lane, warp, rank, pair_in_grp, pairs_in_grp, n_units, n_pair_units);
+    } else {
+      // =========================================== MMA ISSUER ====================================
       const bool leader = elect_one();
-      const uint32_t a_base = smem_u32(s_acopy), w_base = smem_u32(s_w);
-      const uint64_t b1_desc0 = smem_desc(w_base, CG * 16, 128);                               // R1: CG rows per CTA
-      const uint64_t b2_desc0 = smem_desc(w_base + (uint32_t)r1_bytes(CG, g.Kp), (CG / 2) * 16, 128);  // R2: CG/2 rows
-      const uint64_t b1_step = (uint64_t)((CG * 32) >> 4), b2_step = (uint64_t)(((CG / 2) * 32) >> 4);
-      // Forward: zone bounds of this channel group (k0's support pruning), made warp-uniform with a redux so
-      // that the zone loops run on uniform registers.
-#if (LEAFK_EXP & 64)
-      long long dbg_t[3] = {0, 0, 0};
-#endif
-      constexpr int LMAX = CG / 16;
-      int zlo[LMAX], zhi[LMAX], z3r[LMAX], z3f[LMAX];
-      if constexpr (MODE == 0) {
-        const int* z = tm.zones + (size_t)grp * tc::ZONE_INTS;
-#pragma unroll
-        for (int L = 0; L < LMAX; ++L) {
-          zlo[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 2 * L));
-          zhi[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 2 * L + 1));
-          z3r[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 16 + 2 * L));
-          z3f[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 16 + 2 * L + 1));
+      // this CTA's bank image: one bulk copy (TMA) per region, straight into the operand layout k0 wrote; the
+      // generic proxy never touches the bank
+      {
+        size_t off1, len1, off2 = 0, len2 = 0;
+        if constexpr (MODE == 0) {
+          // R1 (main MMA) then R2 (corr MMA), from the group's global image [R1 cta0 | R1 cta1 | R2 cta0 | R2 cta1]
+          const size_t r1 = r1_bytes(CG, g.Kp), r2 = r2_bytes(CG, g.Kp);
+          off1 = (size_t)grp * b_group_bytes(CG, g.Kp) + rank * r1; len1 = r1;
+          off2 = (size_t)grp * b_group_bytes(CG, g.Kp) + 2 * r1 + rank * r2; len2 = r2;
+        } else {
+          off1 = (size_t)grp * t_group_bytes(CG, g.Kp) + rank * t_cta_bytes(CG, g.Kp); len1 = t_cta_bytes(CG, g.Kp);
         }
+        if (leader) {
+          mbar_expect_tx(&misc->bank_full, (uint32_t)(len1 + len2));
+          // <= 64 KB per copy
+          for (size_t o = 0; o < len1; o += 65536)
+            bulk_copy_g2s(s_w + o, w16 + off1 + o, (uint32_t)(len1 - o < 65536 ? len1 - o : 65536), &misc->bank_full);
+          for (size_t o = 0; o < len2; o += 65536)
+            bulk_copy_g2s(s_w + len1 + o, w16 + off2 + o, (uint32_t)(len2 - o < 65536 ? len2 - o : 65536), &misc->bank_full);
+        }
+        __syncwarp();
+        mbar_wait(&misc->bank_full, 0);
+        if (lane == 0) mbar_arrive_rank0(&misc->bank_pair);
       }
-      int it = 0;
-      for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
+      if (rank == 0) {
+        mbar_wait_cluster(&misc->bank_pair, 0);          // the peer's half of the bank rows is resident too
+        const uint32_t a_base = smem_u32(s_acopy), w_base = smem_u32(s_w);
+        // Forward: zone bounds of this channel group (k0's support pruning), made warp-uniform with a redux so
+        // that the zone loops run on uniform registers.
+        constexpr int LMAX = CG / 16;
+        int zlo[LMAX], zhi[LMAX], z3r[LMAX], z3f[LMAX];
+        if constexpr (MODE == 0) {
+          const int* z = tm.zones + (size_t)grp * tc::ZONE_INTS;
+#pragma unroll
+          for (int L = 0; L < LMAX; ++L) {
+            zlo[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 2 * L));
+            zhi[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 2 * L + 1));
+            z3r[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 16 + 2 * L));
+            z3f[L] = __reduce_max_sync(0xffffffffu, __ldg(z + 16 + 2 * L + 1));
+          }
+        }
+        // forward: R1 = CG rows per CTA, R2 = CG/2 rows; training: HI and LO regions of CG/2 rows each
+        const uint64_t b1_desc0 = (MODE == 0) ? smem_desc(w_base, CG * 16, 128) : smem_desc(w_base, (CG / 2) * 16, 128);
+        const uint64_t b2_desc0 = (MODE == 0)
+            ? smem_desc(w_base + (uint32_t)r1_bytes(CG, g.Kp), (CG / 2) * 16, 128)
+            : smem_desc(w_base + (uint32_t)t_region_bytes(CG, g.Kp), (CG / 2) * 16, 128);
+        constexpr uint32_t IDESC_TRAIN = idesc_f16(256, CG);   // M = 256: 128 rows from each CTA of the pair
+        constexpr uint32_t T_STEP = (uint32_t)(((CG / 2) * 32) >> 4);  // descriptor units per k-step slab (training)
+        int it = 0;
+        for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
 #pragma unroll 1
-        for (int p = 0; p < NPHASE; ++p) {
-          const int gp = it * NPHASE + p;
-          const int st = gp % NST;
-#if (LEAFK_EXP & 64)
-          const long long tq0 = clock64();
-#endif
-          mbar_wait_cluster(&misc->a_full[p], (uint32_t)(it & 1));
-#if (LEAFK_EXP & 64)
-          const long long tq1 = clock64();
-#endif
-          mbar_wait_cluster(&misc->acc_empty[st], (uint32_t)(((gp / NST) & 1) ^ 1));
-#if (LEAFK_EXP & 64)
-          const long long tq2 = clock64();
-          dbg_t[0] += tq1 - tq0; dbg_t[1] += tq2 - tq1;
-#endif
-          tc_fence_after();
-          const uint32_t d = tmem + (uint32_t)(st * NB);
-          const uint64_t a_hi = smem_desc(a_base + (uint32_t)((2 * p) * sp.acb), 16, 128);
-          const uint64_t a_lo = smem_desc(a_base + (uint32_t)((2 * p + 1) * sp.acb), 16, 128);
-          if constexpr (MODE == 0) {
+          for (int p = 0; p < NPHASE; ++p) {
+            const int gp = it * NPHASE + p;
+            const int st = gp % NST;
+            mbar_wait_cluster(&misc->a_full[p], (uint32_t)(it & 1));
+            mbar_wait_cluster(&misc->acc_empty[st], (uint32_t)(((gp / NST) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t d = tmem + (uint32_t)(st * NB);
+            const uint64_t a_hi = smem_desc(a_base + (uint32_t)((2 * p) * sp.acb), 16, 128);
+            const uint64_t a_lo = smem_desc(a_base + (uint32_t)((2 * p + 1) * sp.acb), 16, 128);
             if (leader) {
-              // centre zone first (every channel; its first MMA initialises all 2*CG accumulator columns)
-              issue_zone<CG, CG>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo[LMAX - 1], zhi[LMAX - 1] + 1, CG, 0);
-              issue_outer_zones<CG, LMAX - 1>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo, zhi, z3r, z3f);
+              if constexpr (MODE == 0) {
+                // centre zone first (every channel; its first MMA initialises all 2*CG accumulator columns)
+                issue_zone<CG, CG>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo[LMAX - 1], zhi[LMAX - 1] + 1, CG, 0);
+                issue_outer_zones<CG, LMAX - 1>(d, a_hi, a_lo, b1_desc0, b2_desc0, zlo, zhi, z3r, z3f);
+              } else if constexpr (KS > 0) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                  mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)(ks * T_STEP), IDESC_TRAIN, ks > 0);   // x_hi * W_hi
+                  mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b2_desc0 + (uint64_t)(ks * T_STEP), IDESC_TRAIN, 1);        // x_hi * W_lo
+                  mma_f16_ss_pair(d, a_lo + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)(ks * T_STEP), IDESC_TRAIN, 1);        // x_lo * W_hi
+                }
+              } else {
+#pragma unroll 2
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)ks * T_STEP, IDESC_TRAIN, ks > 0);
+                  mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b2_desc0 + (uint64_t)ks * T_STEP, IDESC_TRAIN, 1);
+                  mma_f16_ss_pair(d, a_lo + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)ks * T_STEP, IDESC_TRAIN, 1);
+                }
+              }
               mma_commit_pair(&misc->a_empty[p]);
               mma_commit_pair(&misc->acc_full[st]);
             }
-          } else if (leader) {
-            if (MODE == 1 && ba.skip_xlo) {
-#pragma unroll 4
-              for (int ks = 0; ks < ksteps; ++ks)
-                mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)ks * b1_step, IDESC_MAIN, ks > 0);
-            } else if constexpr (KS > 0) {
-#pragma unroll
-              for (int ks = 0; ks < KS; ++ks) {
-                mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)(ks * ((CG * 32) >> 4)), IDESC_MAIN, ks > 0);
-                mma_f16_ss_pair(d, a_lo + (uint64_t)(2 * ks), b2_desc0 + (uint64_t)(ks * (((CG / 2) * 32) >> 4)), IDESC_CORR, 1);
-              }
-            } else {
-#pragma unroll 2
-              for (int ks = 0; ks < ksteps; ++ks) {
-                mma_f16_ss_pair(d, a_hi + (uint64_t)(2 * ks), b1_desc0 + (uint64_t)ks * b1_step, IDESC_MAIN, ks > 0);
-                mma_f16_ss_pair(d, a_lo + (uint64_t)(2 * ks), b2_desc0 + (uint64_t)ks * b2_step, IDESC_CORR, 1);
-              }
-            }
-            mma_commit_pair(&misc->a_empty[p]);
-            mma_commit_pair(&misc->acc_full[st]);
+            __syncwarp();
           }
-          __syncwarp();
-#if (LEAFK_EXP & 64)
-          dbg_t[2] += clock64() - tq2;
-#endif
         }
       }
-#if (LEAFK_EXP & 64)
-      if (blockIdx.x == 0 && lane == 0)
-        printf("MMA warp: wait a_full %lld, wait acc_empty %lld, issue %lld cycles (tiles %d)\n", dbg_t[0], dbg_t[1], dbg_t[2], it);
-#endif
     }
-  } else if constexpr (MODE == 0) {
-    // =========================================== EPILOGUE (forward) =============================
+  } else {
+    // =========================================== EPILOGUE =========================================
+    if (cpt <= 2) setmaxnreg_inc<200>(); else setmaxnreg_inc<176>();
     const int e = warp, q = e & 3, hh = e >> 2;
     const int etid = tid;                               // 0..255
     const int m = 32 * q + lane;                        // accumulator row
-    // this thread's filters: sorted positions hh*FPT + i of the group; perm gives the filter they belong to
-    const int* gperm = tm.perm + (size_t)grp * (CG / 2);
-#if (LEAFK_EXP & 64)
-    long long dbg_e[5] = {0, 0, 0, 0, 0};
-#endif
-    float pa[FPT];
-#pragma unroll
-    for (int i = 0; i < FPT; ++i) {
-      const int f = __ldg(gperm + hh * FPT + i);
-      pa[i] = (f < g.F) ? __ldg(cprm + (size_t)f * 8 + CP_POOLA) : -1.0f;
-    }
     const float centre = 0.5f * (float)(g.K - 1);
     const int n_last = g.n_begin + g.n_count - 1;
-    float* red = s_red + (size_t)e * FPT * 33;          // this warp's transpose buffer (generic tile-end row sums)
+    float* red = s_red + (size_t)e * NV * 33;           // this warp's transpose buffer (generic tile-end row sums)
     int sig_b = -1;                                     // clip whose last stored tile K2 has not been told about yet
-    const int red_fi = halving_index<FPT, 16>(lane);    // filter whose row sum the halving reduction leaves in this lane
-    // output table of the tile-end store (slot fastest, the layout K2 reads); read back by the same threads only
-    for (int idx = etid; idx < g.SL * (CG / 2); idx += EPI_WARPS * 32) {
-      const int fl = idx / g.SL, slot = idx - fl * g.SL;
-      const int f = __ldg(gperm + fl);                      // sorted position -> filter
-      int4 o = make_int4(((fl / FPT) * 4 * g.SL + slot) * FPT + fl % FPT, -1, 0, 0);
-      if (f < g.F) { o.y = f * g.SL + slot; o.z = (int)__ldg(cprm + (size_t)f * 8 + CP_WSCALE); }
-      s_out[idx] = o;
+    const int FV = (MODE == 0) ? g.F : 4 * g.F;         // virtual filters per (clip, tile) block of partial sums
+
+    // per-thread filter constants and the output table of the tile-end store (slot fastest, the layout K2 reads);
+    // the table is read back by the same threads only
+    constexpr int NF = (MODE == 0) ? NV : NV / 4;       // real filters per thread
+    float pa[NF];
+    if constexpr (MODE == 0) {
+      // this thread's filters: sorted positions hh*NV + i of the group; perm gives the filter they belong to
+      const int* gperm = tm.perm + (size_t)grp * (CG / 2);
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const int f = __ldg(gperm + hh * NV + i);
+        pa[i] = (f < g.F) ? __ldg(cprm + (size_t)f * 8 + CP_POOLA) : -1.0f;
+      }
+      for (int idx = etid; idx < g.SL * (CG / 2); idx += EPI_WARPS * 32) {
+        const int fl = idx / g.SL, slot = idx - fl * g.SL;
+        const int f = __ldg(gperm + fl);                      // sorted position -> filter
+        int4 o = make_int4(((fl / NV) * 4 * g.SL + slot) * NV + fl % NV, -1, 0, 0);
+        if (f < g.F) { o.y = f * g.SL + slot; o.z = 2 * (int)__ldg(cprm + (size_t)f * 8 + CP_WSCALE); }
+        s_out[idx] = o;
+      }
+    } else {
+      constexpr int FB = CG / 6;
+      const int fbase = grp * FB + hh * NF;             // first filter of this thread
+#pragma unroll
+      for (int i = 0; i < NF; ++i) pa[i] = __ldg(ta.tprm + (size_t)(fbase + i) * 8);
+      // entries: (column half h2, virtual filter vi = kind*NF + i, slot)
+      for (int idx = etid; idx < g.SL * 2 * NV; idx += EPI_WARPS * 32) {
+        const int vl = idx / g.SL, slot = idx - vl * g.SL;
+        const int h2 = vl / NV, vi = vl - h2 * NV, kind = vi / NF, i = vi - kind * NF;
+        const int f = grp * FB + h2 * NF + i;
+        int4 o = make_int4(((h2 * 4) * g.SL + slot) * NV + vi, -1, 0, 0);
+        if (f < g.F) {
+          const float* tp = ta.tprm + (size_t)f * 8;
+          const int shy = (int)__ldg(tp + 1), shz = (int)__ldg(tp + 2), shv = (int)__ldg(tp + 3);
+          o.y = (kind * g.F + f) * g.SL + slot;
+          o.z = shy + (kind == 1 ? shz : (kind == 2 ? shv : shy));
+        }
+        s_out[idx] = o;
+      }
     }
+
     int it = 0;
     for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
       const long long u = 2 * pu + rank;
@@ -522,9 +645,9 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       const int n_first = first_frame_of(g, ts);
       const long long tb = ts + 8 * m;                  // this row's 8 samples: tb .. tb+7
       const int nb = first_frame_of(g, tb);
-      float acc[FPT][NSLOT];
+      float acc[NV][NSLOT];
 #pragma unroll
-      for (int i = 0; i < FPT; ++i)
+      for (int i = 0; i < NV; ++i)
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) acc[i][j] = 0.f;
 
@@ -542,39 +665,52 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
           const float kc = (float)k - centre;
           dj[j] = ok ? kc * kc : 1.0e30f;               // ex2(pa * 1e30) = 0: outside the window
         }
-#if (LEAFK_EXP & 64)
-        const long long te0 = clock64();
-#endif
         mbar_wait(&misc->acc_full[st], (uint32_t)((gp / NST) & 1));
-#if (LEAFK_EXP & 64)
-        const long long te1 = clock64();
-        dbg_e[0] += te1 - te0;
-#endif
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + hh * (CG / 2));
-        const uint32_t tlo = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + 2 * CG - 8 - hh * (CG / 2));
+        if constexpr (MODE == 0) {
+          const uint32_t tlo = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + 2 * CG - 8 - hh * (CG / 2));
 #pragma unroll
-        for (int c = 0; c < (((LEAFK_EXP & 1) || ((LEAFK_EXP & 16) && q == 0) || ((LEAFK_EXP & 32) && q != 0)) ? 0 : FPT / 4); ++c) {
-          // hi products of the 4 filters at columns hh*CG/2 + 8c ..; their lo products sit in the mirrored
-          // 8-column block of the lo half, filters in reverse order (k1_tc_layout.cuh)
-          float ym[8], yc[8];
-          if constexpr ((LEAFK_EXP & 8) != 0) {            // experiment: the arithmetic without the TMEM loads
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { ym[i] = dj[0] * (float)(i + c); yc[i] = dj[1] + (float)i; }
-          } else {
+          for (int c = 0; c < NV / 4; ++c) {
+            // hi products of the 4 filters at columns hh*CG/2 + 8c ..; their lo products sit in the mirrored
+            // 8-column block of the lo half, filters in reverse order (k1_tc_layout.cuh)
+            float ym[8], yc[8];
             tmem_ld8x2_sync(taddr + 8 * c, tlo - 8 * c, ym, yc);
-          }
-          if constexpr ((LEAFK_EXP & 4) != 0) {            // experiment: the TMEM loads without the arithmetic
-            acc[0][0] += ym[0] + yc[7];
-            continue;
-          }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float re = ym[2 * i] + yc[2 * (3 - i)], im = ym[2 * i + 1] + yc[2 * (3 - i) + 1];
-            const float en = fmaf(re, re, im * im);
+            for (int i = 0; i < 4; ++i) {
+              const float re = ym[2 * i] + yc[2 * (3 - i)], im = ym[2 * i + 1] + yc[2 * (3 - i) + 1];
+              const float en = fmaf(re, re, im * im);
 #pragma unroll
-            for (int j = 0; j < NSLOT; ++j)
-              acc[4 * c + i][j] = fmaf(ex2_approx(pa[4 * c + i] * dj[j]), en, acc[4 * c + i][j]);
+              for (int j = 0; j < NSLOT; ++j)
+                acc[4 * c + i][j] = fmaf(ex2_approx(pa[4 * c + i] * dj[j]), en, acc[4 * c + i][j]);
+            }
+          }
+        } else {
+          constexpr int FB = CG / 6;
+          float dv[NSLOT];                                // (k - c)^2 inside the window, 0 outside
+#pragma unroll
+          for (int j = 0; j < NSLOT; ++j) dv[j] = dj[j] < 1.0e29f ? dj[j] : 0.f;
+#pragma unroll
+          for (int c = 0; c < NF / 4; ++c) {
+            // y, z, v accumulators (all three split products already summed in tensor memory) of 4 filters
+            float yv[8], zv[8], vv[8];
+            tmem_ld8x3_sync(taddr + 8 * c, taddr + FB + 8 * c, taddr + 2 * FB + 8 * c, yv, zv, vv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int fi = 4 * c + i;
+              const float yre = yv[2 * i], yim = yv[2 * i + 1];
+              const float en = fmaf(yre, yre, yim * yim);
+              const float qm = fmaf(yim, zv[2 * i], -(yre * zv[2 * i + 1]));
+              const float qs = fmaf(yre, vv[2 * i], yim * vv[2 * i + 1]);
+#pragma unroll
+              for (int j = 0; j < NSLOT; ++j) {
+                const float wgt = ex2_approx(pa[fi] * dj[j]);
+                acc[fi][j] = fmaf(wgt, en, acc[fi][j]);
+                acc[NF + fi][j] = fmaf(wgt, qm, acc[NF + fi][j]);
+                acc[2 * NF + fi][j] = fmaf(wgt, qs, acc[2 * NF + fi][j]);
+                acc[3 * NF + fi][j] = fmaf(wgt * dv[j], en, acc[3 * NF + fi][j]);
+              }
+            }
           }
         }
         tc_fence_before();
@@ -586,228 +722,21 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
           if (lane == 0) atomicAdd(tm.done + sig_b, 1);
           sig_b = -1;
         }
-#if (LEAFK_EXP & 64)
-        dbg_e[1] += clock64() - te1;
-#endif
       }
-#if (LEAFK_EXP & 64)
-      const long long te2 = clock64();
-#endif
 
-      // ---- reduce over the rows of this warp: per-frame sums -> s_pw[buf][e][slot][fi] ----------
-      // This section is on the critical path: while the epilogue warps are in it nobody drains the accumulator
-      // stages, and the three stages cover only ~8 k cycles of MMAs.  The shared-memory pipe is ~86 % busy with
-      // tensor-core operand fetches, so every dependent trip through it (shuffle level, store/load pair) costs
-      // 150-350 cycles: the row sums therefore run as ONE recursive-halving reduction over all (<= 5) frames at once
-      // -- 5 dependent shuffle levels per tile instead of 5 per frame or per (frame, filter).
-      float* pw_buf = s_pw + (size_t)(it & 1) * (EPI_WARPS * g.SL * FPT);
-      float* pw = pw_buf + (size_t)e * g.SL * FPT;
-      for (int i = lane; i < g.SL * FPT; i += 32) pw[i] = 0.f;
-      __syncwarp();
-      const int nb_lo = __shfl_sync(0xffffffffu, nb, 0);
-      int nb_hi = __shfl_sync(0xffffffffu, nb, 31) + NSLOT - 1;
-      constexpr int NFR = NSLOT + 2;                        // frames the fast path covers
-      if (NSLOT == 3 && nb_hi - nb_lo < NFR) {
-        if (nb_hi > n_last) nb_hi = n_last;
-        const int eo = nb - nb_lo;                          // 0..2: this lane's first frame relative to the warp's
-        constexpr int H1 = (FPT + 1) / 2;
-        const bool up = (lane & 16) != 0;
-        float k1[NFR][H1];
-#pragma unroll
-        for (int d = 0; d < NFR; ++d) {
-#pragma unroll
-          for (int i = 0; i < H1; ++i) {
-            float lo_v = 0.f, hi_v = 0.f;
-#pragma unroll
-            for (int jj = 0; jj < NSLOT; ++jj) {
-              if (d - jj >= 0 && d - jj <= 2) {             // frame d is slot jj of the lanes with eo == d - jj
-                lo_v = (eo == d - jj) ? acc[i][jj] : lo_v;
-                if (i + H1 < FPT) hi_v = (eo == d - jj) ? acc[i + H1 < FPT ? i + H1 : 0][jj] : hi_v;
-              }
-            }
-            k1[d][i] = (up ? hi_v : lo_v) + __shfl_xor_sync(0xffffffffu, up ? lo_v : hi_v, 16);
-          }
-        }
-        float tot[NFR];
-        halving_multi<NFR, H1, 8>(k1, lane, tot);
-#pragma unroll
-        for (int d = 0; d < NFR; ++d) {
-          const int slot = nb_lo + d - n_first;
-          if (red_fi >= 0 && nb_lo + d <= nb_hi && slot < g.SL) pw[slot * FPT + red_fi] = tot[d];
-        }
-      } else {
-        // generic geometry (more frames per warp): row sums through the transpose buffer, one frame at a time
-        if (nb_hi > n_last) nb_hi = n_last;
-        for (int n = nb_lo; n <= nb_hi; ++n) {
-          const int slot = n - n_first;
-          if (slot >= g.SL) break;
-          const int j = n - nb;
-#pragma unroll
-          for (int i = 0; i < FPT; ++i) {
-            float v = 0.f;
-#pragma unroll
-            for (int jj = 0; jj < NSLOT; ++jj) v = (j == jj) ? acc[i][jj] : v;
-            red[i * 33 + lane] = v;
-          }
-          __syncwarp();
-          if (lane < FPT) {
-            const float* rr = red + lane * 33;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int r = 0; r < 32; r += 4) { s0 += rr[r]; s1 += rr[r + 1]; s2 += rr[r + 2]; s3 += rr[r + 3]; }
-            pw[slot * FPT + lane] = (s0 + s1) + (s2 + s3);
-          }
-          __syncwarp();
-        }
-      }
-#if (LEAFK_EXP & 64)
-      const long long te3 = clock64();
-      dbg_e[3] += te3 - te2;
-#endif
+      // ---- tile end: row sums of this warp -> s_pw[buf][e][slot][vi], then the quadrant sum and the store --------
+      float* pw_buf = s_pw + (size_t)(it & 1) * (EPI_WARPS * g.SL * NV);
+      tile_end_rowsums<NV, NSLOT>(acc, pw_buf + (size_t)e * g.SL * NV, red, lane, nb, n_first, n_last, g.SL);
       named_bar_sync(BAR_EPI, EPI_WARPS * 32);
-      // ---- fixed-order sum over the four row quadrants, undo the scaling, store -----------------
       const int sx = misc->sx_ring[it & 3];
-      float* dst = ppart + ((size_t)b * g.n_tiles + tile) * g.SL * g.F;
-      for (int idx = etid; idx < g.SL * (CG / 2); idx += EPI_WARPS * 32) {
-        const int4 o = s_out[idx];
-        if (valid && o.y >= 0) {
-          const float* src = pw_buf + o.x;
-          float s = 0.f;
-#pragma unroll
-          for (int qq = 0; qq < 4; ++qq) s += src[(size_t)qq * g.SL * FPT];
-          dst[o.y] = scalbnf(s, -2 * (sx + o.z));
-        }
-      }
+      float* dst = ppart + ((size_t)b * g.n_tiles + tile) * g.SL * FV;
+      tile_end_store(pw_buf, s_out, g.SL * 2 * NV, etid, valid, dst, sx, g.SL * NV);
       sig_b = (valid && tm.done != nullptr) ? b : -1;   // published off the critical path (phase 1 of the next tile)
-#if (LEAFK_EXP & 64)
-      dbg_e[2] += clock64() - te2;
-#endif
     }
     if (sig_b >= 0) {
       __threadfence();
       __syncwarp();
       if (lane == 0) atomicAdd(tm.done + sig_b, 1);
-    }
-#if (LEAFK_EXP & 64)
-    if (blockIdx.x == 0 && tid == 0)
-      printf("epilogue warp 0: wait acc_full %lld, phase work %lld, tile end %lld (reduction %lld) cycles\n", dbg_e[0], dbg_e[1], dbg_e[2], dbg_e[3]);
-#endif
-  } else {
-    // =========================================== EPILOGUE (backward) ============================
-    constexpr int FB = CG / 6;                          // filters per group
-    constexpr int FPB = FB / 2;                         // filters per epilogue thread
-    const int e = warp, q = e & 3, hh = e >> 2;
-    const int m = 32 * q + lane;
-    const int fbase = grp * FB + hh * FPB;              // first filter of this thread
-    float pa[FPB];
-    int shy[FPB], shz[FPB], shv[FPB];
-#pragma unroll
-    for (int i = 0; i < FPB; ++i) {
-      const float* bp = ba.bprm + (size_t)(fbase + i) * 8;
-      pa[i] = __ldg(bp + 0);
-      shy[i] = (int)__ldg(bp + 1); shz[i] = (int)__ldg(bp + 2); shv[i] = (int)__ldg(bp + 3);
-    }
-    float a_mu[FPB], a_sg[FPB], a_pw[FPB];
-#pragma unroll
-    for (int i = 0; i < FPB; ++i) { a_mu[i] = 0.f; a_sg[i] = 0.f; a_pw[i] = 0.f; }
-    const float centre = 0.5f * (float)(g.K - 1);
-    const int n_last = g.n_begin + g.n_count - 1;
-    int it = 0;
-    for (long long pu = pair_in_grp; pu < n_pair_units; pu += pairs_in_grp, ++it) {
-      const long long u = 2 * pu + rank;
-      const bool valid = u < n_units;
-      const int b = valid ? (int)(u / g.n_tiles) : 0, tile = valid ? (int)(u % g.n_tiles) : 0;
-      const long long ts = g.te_lo + (long long)tile * TILE;
-      const long long te = !valid ? ts : ((ts + TILE < g.te_hi) ? ts + TILE : g.te_hi);   // invalid unit: all rows masked
-      const long long tb = ts + 8 * m;
-      const int nb = first_frame_of(g, tb);
-      float dpv[NSLOT][FPB];
-#pragma unroll
-      for (int j = 0; j < NSLOT; ++j) {
-        const int n = nb + j;
-        const bool nok = (n >= g.n_begin) && (n <= n_last);
-        const float* row = ba.dpT + ((size_t)b * g.N_total + (nok ? n : 0)) * g.F;
-#pragma unroll
-        for (int i = 0; i < FPB; ++i) dpv[j][i] = (nok && fbase + i < g.F) ? __ldg(row + fbase + i) : 0.f;
-      }
-      float sy[FPB], sz[FPB], sv[FPB];
-      bool have_scale = false;
-#pragma unroll 1
-      for (int p = 0; p < NPHASE; ++p) {
-        const int gp = it * NPHASE + p;
-        const int st = gp % NST;
-        const long long t = tb + p;
-        float dj[NSLOT];
-#pragma unroll
-        for (int j = 0; j < NSLOT; ++j) {
-          const int n = nb + j;
-          const long long k = t + g.padL - (long long)n * g.H;
-          const bool ok = (k >= 0) && (k < g.K) && (t < te) && (n <= n_last);
-          const float kc = (float)k - centre;
-          dj[j] = ok ? kc * kc : 1.0e30f;
-        }
-        mbar_wait(&misc->acc_full[st], (uint32_t)((gp / NST) & 1));
-        tc_fence_after();
-        if (!have_scale) {                                 // sx of this tile is published before its first phase
-          const int sx = misc->sx_ring[it & 3];
-#pragma unroll
-          for (int i = 0; i < FPB; ++i) {
-            sy[i] = scalbnf(1.0f, -(sx + shy[i])); sz[i] = scalbnf(1.0f, -(sx + shz[i])); sv[i] = scalbnf(1.0f, -(sx + shv[i]));
-          }
-          have_scale = true;
-        }
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + hh * (CG / 2));
-#pragma unroll
-        for (int c = 0; c < FPB / 4; ++c) {
-          float ym[8], yc[8], zm[8], zc[8], vm[8], vc[8];
-          tmem_ld8x2_sync(taddr + 8 * c, taddr + CG + 8 * c, ym, yc);
-          tmem_ld8x2_sync(taddr + FB + 8 * c, taddr + CG + FB + 8 * c, zm, zc);
-          tmem_ld8x2_sync(taddr + 2 * FB + 8 * c, taddr + CG + 2 * FB + 8 * c, vm, vc);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int fi = 4 * c + i;
-            const float yre = (ym[2 * i] + yc[2 * i]) * sy[fi], yim = (ym[2 * i + 1] + yc[2 * i + 1]) * sy[fi];
-            const float zre = (zm[2 * i] + zc[2 * i]) * sz[fi], zim = (zm[2 * i + 1] + zc[2 * i + 1]) * sz[fi];
-            const float vre = (vm[2 * i] + vc[2 * i]) * sv[fi], vim = (vm[2 * i + 1] + vc[2 * i + 1]) * sv[fi];
-            float de = 0.f, dgs = 0.f;
-#pragma unroll
-            for (int j = 0; j < NSLOT; ++j) {
-              const float wgt = ex2_approx(pa[fi] * dj[j]) * dpv[j][fi];
-              de += wgt;
-              dgs = fmaf(wgt, dj[j] < 1.0e29f ? dj[j] : 0.f, dgs);
-            }
-            const float en = fmaf(yre, yre, yim * yim);
-            a_mu[fi] = fmaf(de, yim * zre - yre * zim, a_mu[fi]);
-            a_sg[fi] = fmaf(de, yre * vre + yim * vim, a_sg[fi]);
-            a_pw[fi] = fmaf(en, dgs, a_pw[fi]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_rank0(&misc->acc_empty[st]);
-      }
-    }
-    // ---- CTA reduction of the 3*FPB sums per thread -> one partial row per filter ----------------
-    float* red = s_pw;                                  // [8 warps][32]
-#pragma unroll
-    for (int i = 0; i < FPB; ++i) {
-      float v0 = a_mu[i], v1 = a_sg[i], v2 = a_pw[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
-      }
-      if (lane == 0) { red[e * 32 + 3 * i] = v0; red[e * 32 + 3 * i + 1] = v1; red[e * 32 + 3 * i + 2] = v2; }
-    }
-    named_bar_sync(BAR_EPI, EPI_WARPS * 32);
-    if (tid < 2 * FPB * 3) {
-      const int h2 = tid / (FPB * 3), r = tid % (FPB * 3);
-      float sacc = 0.f;
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) sacc += red[(h2 * 4 + qq) * 32 + r];
-      const int f = grp * FB + h2 * FPB + r / 3;
-      ba.bpart[((size_t)cta_in_grp * ba.Fpad + f) * 4 + (r % 3)] = sacc;
     }
   }
 
@@ -816,10 +745,8 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
   cluster_sync_all();                        // nobody may still signal a peer barrier / use TMEM
   if (warp == tc::MMA_WARP) tmem_dealloc_pair<512>(tmem);
   if (rdy.perf != nullptr && blockIdx.x == 0 && tid == 0) {
-    long long t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     rdy.perf[0] = clock64() - perf_c0;
-    rdy.perf[1] = t1 - perf_t0;
+    rdy.perf[1] = global_timer_ns() - perf_t0;
   }
 }
 
@@ -836,52 +763,12 @@ bool k1_tc_supported(const Geom& g, const char** why) {
   return true;
 }
 
-template <int CG, int NSLOT, int KS>
-static cudaError_t launch_inst_ks(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
-                                  int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy, const TcMap& tm) {
-  // the opt-in to > 48 KB of dynamic shared memory is per function and device: raise it only when this launch needs
-  // more than any earlier one asked for (a driver call per forward otherwise)
-  static thread_local int smem_set[64] = {0};
-  int dev = 0;
-  cudaError_t err = cudaGetDevice(&dev);
-  if (err != cudaSuccess) return err;
-  if (dev < 0 || dev >= 64 || smem_set[dev] < smem) {
-    err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 0, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (err != cudaSuccess) return err;
-    if (dev >= 0 && dev < 64) smem_set[dev] = smem;
-  }
-  TcBwdArgs none{nullptr, nullptr, nullptr, 0, 0};
-  cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(tc::NTHREADS); lc.dynamicSmemBytes = (size_t)smem; lc.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // may start under the tail of k0 (see kernel)
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  lc.attrs = at; lc.numAttrs = 1;
-  return cudaLaunchKernelEx(&lc, k1_tc_kernel<CG, NSLOT, 0, KS>, g, x, w16, cprm, ppart, n_groups, none, rdy, tm);
-}
-template <int CG, int NSLOT>
-static cudaError_t launch_inst(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
-                               int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy, const TcMap& tm) {
-  return launch_inst_ks<CG, NSLOT, 0>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy, tm);
-}
-
-template <int CG, int NSLOT, int KS>
-static cudaError_t launch_bwd_inst_ks(const Geom& g, const float* x, const uint8_t* w16, int n_groups, int grid,
-                                      const TcBwdArgs& ba, cudaStream_t stream) {
-  const int smem = tc::smem_plan(CG, g.Kp, g.SL, 1).total;
-  cudaError_t err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, 1, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (err != cudaSuccess) return err;
-  k1_tc_kernel<CG, NSLOT, 1, KS><<<grid, tc::NTHREADS, smem, stream>>>(g, x, w16, nullptr, nullptr, n_groups, ba,
-                                                                       TcReady{nullptr, 1, nullptr}, TcMap{nullptr, nullptr, nullptr});
-  return cudaGetLastError();
-}
-template <int CG, int NSLOT>
-static cudaError_t launch_bwd_inst(const Geom& g, const float* x, const uint8_t* w16, int n_groups, int grid,
-                                   const TcBwdArgs& ba, cudaStream_t stream) {
-  if constexpr (CG == 96) {
-    if (g.Kp == 26 * tc::KSTEP) return launch_bwd_inst_ks<CG, NSLOT, 26>(g, x, w16, n_groups, grid, ba, stream);
-  }
-  return launch_bwd_inst_ks<CG, NSLOT, 0>(g, x, w16, n_groups, grid, ba, stream);
+// filters per group of the training kernel for this geometry (0: not covered -> generic fp32 backward)
+int k1_tc_train_filters_per_group(int K, int H) {
+  const int Kp = (K + 15) / 16 * 16;
+  if (Kp > 2048) return 0;
+  const int SL = (tc::TILE + K - 2) / H + 1;
+  return tc::train_filters_per_group(Kp, SL, tc::slots_per_thread(K, H));
 }
 
 static int sm_count(cudaError_t* err) {
@@ -898,36 +785,67 @@ static int sm_count(cudaError_t* err) {
   return dev < 64 ? n_sm_cached[dev] : 148;
 }
 
-// Backward correlation pass: FB filters per group (16 -> CG 96, 8 -> CG 48).  Returns the number of CTAs per
-// group through *ctas_per_group (rows of bpart the final reduction must add).
-cudaError_t launch_k1_tc_bwd(const Geom& g, const float* x, const uint8_t* w16b, int FB, int n_groups,
-                             const float* dpT, const float* bprm, float* bpart, int* ctas_per_group,
-                             int skip_xlo, cudaStream_t stream) {
+template <int CG, int NSLOT, int MODE, int KS>
+static cudaError_t launch_inst(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
+                               int n_groups, int grid, int smem, cudaStream_t stream, const TcTrainArgs& ta,
+                               const TcReady& rdy, const TcMap& tm) {
+  // the opt-in to > 48 KB of dynamic shared memory is per function and device: raise it only when this launch needs
+  // more than any earlier one asked for (a driver call per forward otherwise)
+  static thread_local int smem_set[64] = {0};
+  int dev = 0;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return err;
+  if (dev < 0 || dev >= 64 || smem_set[dev] < smem) {
+    err = cudaFuncSetAttribute(k1_tc_kernel<CG, NSLOT, MODE, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    if (dev >= 0 && dev < 64) smem_set[dev] = smem;
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(tc::NTHREADS); lc.dynamicSmemBytes = (size_t)smem; lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;       // may start under the tail of k0 (see kernel)
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, k1_tc_kernel<CG, NSLOT, MODE, KS>, g, x, w16, cprm, ppart, n_groups, ta, rdy, tm);
+}
+
+// Training forward: FB filters per group (16 -> CG 96, 8 -> CG 48); partial sums of the 4 pooled quantities go to
+// ppart[b][tile][kind*F + f][slot].
+cudaError_t launch_k1_tc_train(const Geom& g, const float* x, const uint8_t* w16t, int FB, int n_groups,
+                               const float* tprm, float* ppart, int* done, cudaStream_t stream) {
   cudaError_t err;
   const int n_sm = sm_count(&err);
   if (err != cudaSuccess) return err;
   const int grid = tc::pair_grid(n_sm, n_groups, (long long)g.B * g.n_tiles);
-  *ctas_per_group = 2 * (((grid / 2) + n_groups - 1) / n_groups);   // rows of bpart (zero-filled by the caller)
-  TcBwdArgs ba{dpT, bprm, bpart, n_groups * FB, skip_xlo};
+  const TcTrainArgs ta{tprm, n_groups * FB};
+  const TcReady rdy{nullptr, 1, nullptr, nullptr};
+  const TcMap tm{done, nullptr, nullptr};
   const int nslot = tc::slots_per_thread(g.K, g.H);
-  if (FB == 16 && nslot <= 3) return launch_bwd_inst<96, 3>(g, x, w16b, n_groups, grid, ba, stream);
-  if (FB == 8 && nslot <= 3) return launch_bwd_inst<48, 3>(g, x, w16b, n_groups, grid, ba, stream);
-  if (FB == 8 && nslot <= 5) return launch_bwd_inst<48, 5>(g, x, w16b, n_groups, grid, ba, stream);
+  if (FB == 16 && nslot <= 3) {
+    const int smem = tc::smem_plan(96, g.Kp, g.SL, 1, 3).total;
+    if (g.Kp == 26 * tc::KSTEP) return launch_inst<96, 3, 1, 26>(g, x, w16t, nullptr, ppart, n_groups, grid, smem, stream, ta, rdy, tm);
+    return launch_inst<96, 3, 1, 0>(g, x, w16t, nullptr, ppart, n_groups, grid, smem, stream, ta, rdy, tm);
+  }
+  if (FB == 8 && nslot <= 5) {
+    const int smem = tc::smem_plan(48, g.Kp, g.SL, 1, 5).total;
+    return launch_inst<48, 5, 1, 0>(g, x, w16t, nullptr, ppart, n_groups, grid, smem, stream, ta, rdy, tm);
+  }
   return cudaErrorNotSupported;
 }
 
 template <int CG>
 static cudaError_t launch_cg(int nslot, const Geom& g, const float* x, const uint8_t* w16, const float* cprm,
                              float* ppart, int n_groups, int grid, int smem, cudaStream_t stream, const TcReady& rdy, const TcMap& tm) {
-  if (nslot <= 3) return launch_inst<CG, 3>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy, tm);
-  if constexpr (CG <= 64) return launch_inst<CG, 5>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, rdy, tm);
+  const TcTrainArgs none{nullptr, 0};
+  if (nslot <= 3) return launch_inst<CG, 3, 0, 0>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, none, rdy, tm);
+  if constexpr (CG <= 64) return launch_inst<CG, 5, 0, 0>(g, x, w16, cprm, ppart, n_groups, grid, smem, stream, none, rdy, tm);
   return cudaErrorNotSupported;
 }
 
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm, float* ppart,
                          int tc_cg, int tc_groups, const int* tc_perm, const int* tc_zones, int* done, cudaStream_t stream,
-                         const int* ready, int clips_per_flag, long long* perf) {
-  const TcReady rdy{ready, clips_per_flag < 1 ? 1 : clips_per_flag, perf};
+                         const int* ready, int clips_per_flag, long long* perf, int* err_word) {
+  const TcReady rdy{ready, clips_per_flag < 1 ? 1 : clips_per_flag, perf, err_word};
   const TcMap tm{done, tc_perm, tc_zones};
   cudaError_t err;
   const int n_sm = sm_count(&err);

@@ -69,14 +69,6 @@ __host__ __device__ inline size_t r2_bytes(int CG, int Kp) { return (size_t)Kp *
 __host__ __device__ inline size_t b_cta_bytes(int CG, int Kp) { return r1_bytes(CG, Kp) + r2_bytes(CG, Kp); }
 __host__ __device__ inline size_t b_group_bytes(int CG, int Kp) { return 2 * b_cta_bytes(CG, Kp); }
 
-// byte offsets, inside a group's global image, of channel c / tap k:
-__host__ __device__ inline size_t g_hi_main(int CG, int Kp, int c, int k) { return region_offset(CG, c, k); }
-__host__ __device__ inline size_t g_lo_main(int CG, int Kp, int c, int k) { return r1_bytes(CG, Kp) + region_offset(CG, c, k); }
-__host__ __device__ inline size_t g_hi_corr(int CG, int Kp, int c, int k) {
-  const int h = CG / 2;
-  return 2 * r1_bytes(CG, Kp) + (size_t)(c / h) * r2_bytes(CG, Kp) + region_offset(h, c % h, k);
-}
-
 // ---- pruned forward layout: byte offsets inside a group's global image for sorted channel c = 2*j + ri -------
 // (FG = CG/2 filters per group, j = sorted position in the group, na1 / na3 = active channels of the k-step, k = tap)
 __host__ __device__ inline size_t p_hi_main(int CG, int Kp, int c, int na1, int na3, int k) {
@@ -119,6 +111,21 @@ __host__ __device__ inline int slot_of(int rank, int n_groups) { return rank / n
 constexpr int ZONE_INTS = 32;       // ints per channel group in the zone table: [0,16) {lo_L, hi_L} of na1, L = 1..CG/16 <= 6;
                                     // [16,32) {na3 on level L's rising zone, on its falling zone}
 
+// TRAINING LAYOUT (mode 1).  A group holds FB filters x 3 kinds (h, tau*h, (tau^2/sigma^3 - 1/sigma)*h) x (re, im)
+// = CG = 6*FB channels (train_channel()).  All three split products of a k-step accumulate into the SAME CG
+// accumulator columns with three MMAs of N = CG:  x_hi*W_hi (accumulate = k-step > 0),  x_hi*W_lo,  x_lo*W_hi.
+// Each CTA of the pair supplies the bank rows of its own half of the columns (CTA r: columns [r*CG/2, (r+1)*CG/2)),
+// so per CTA the bank is two regions of CG/2 rows -- HI then LO -- in the k-step-slab layout of region_offset();
+// the third MMA reads the HI region again.  Global image of a group: [HI cta0 | LO cta0 | HI cta1 | LO cta1].
+__host__ __device__ inline size_t t_region_bytes(int CG, int Kp) { return (size_t)Kp * (CG / 2) * 2; }
+__host__ __device__ inline size_t t_cta_bytes(int CG, int Kp) { return 2 * t_region_bytes(CG, Kp); }
+__host__ __device__ inline size_t t_group_bytes(int CG, int Kp) { return 2 * t_cta_bytes(CG, Kp); }
+__host__ __device__ inline size_t t_hi(int CG, int Kp, int c, int k) {
+  const int h = CG / 2;
+  return (size_t)(c / h) * t_cta_bytes(CG, Kp) + region_offset(h, c % h, k);
+}
+__host__ __device__ inline size_t t_lo(int CG, int Kp, int c, int k) { return t_hi(CG, Kp, c, k) + t_region_bytes(CG, Kp); }
+
 // Byte offsets of the kernel's dynamic shared memory regions.
 struct SmemPlan {
   int CL;          // halves per shifted copy: 8*127 + Kp
@@ -127,23 +134,28 @@ struct SmemPlan {
   int off_w, off_acopy, off_pw, off_red, off_out, off_misc, total;
 };
 
-// mode 0: forward (pooling partial buffers), mode 1: backward (small reduction scratch instead)
+// Virtual filters per epilogue thread: forward CG/4 filters; training (mode 1) FB/2 filters x 4 pooled quantities
+// (e, q_mu, q_sigma, q_poolw), FB = CG/6 filters per group.
+__host__ __device__ constexpr int virt_per_thread(int CG, int mode) { return mode == 0 ? CG / 4 : 4 * (CG / 12); }
+
+// mode 0: forward, mode 1: training forward (banks h, tau*h, (tau^2/sigma^3 - 1/sigma)*h; see "TRAINING LAYOUT")
 __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode = 0, int nslot = 3) {
   SmemPlan s;
   s.CL = 8 * 127 + Kp;
   s.LX = s.CL + 8;
   s.acb = s.CL * 2;
+  const int NV = virt_per_thread(CG, mode);
   int off = 0;
-  s.off_w = off;      off += (int)b_cta_bytes(CG, Kp);       // R1 | R2 of this CTA
+  s.off_w = off;      off += (mode == 0) ? (int)b_cta_bytes(CG, Kp) : (int)t_cta_bytes(CG, Kp);
   s.off_acopy = off;  off += 16 * s.acb;
-  s.off_pw = off;     off += (mode == 0) ? 2 * 8 * SL * (CG / 4) * 4 : 8 * 32 * 4;
-  // forward: per epilogue warp a (CG/4 filters) x 33 float transpose buffer (generic tile-end row sums)
+  s.off_pw = off;     off += 2 * 8 * SL * NV * 4;          // two buffers of per-warp row sums [8 warps][SL][NV]
+  // per epilogue warp an NV x 33 float transpose buffer (generic tile-end row sums)
   s.off_red = (off + 15) / 16 * 16;
-  // forward: per (filter, slot) output of a tile {offset in the reduction buffer, offset in the tile's partial-sum
-  // block or -1, bank scale of the filter, 0}: tile independent, built once per CTA
-  s.off_out = s.off_red + ((mode == 0) ? 8 * (CG / 4) * 33 * 4 : 0);
+  // per (virtual filter, slot) output of a tile {offset in the reduction buffer, offset in the tile's partial-sum
+  // block or -1, power-of-two exponent of the bank scaling, 0}: tile independent, built once per CTA
+  s.off_out = s.off_red + 8 * NV * 33 * 4;
   s.off_out = (s.off_out + 15) / 16 * 16;
-  s.off_misc = s.off_out + ((mode == 0) ? SL * (CG / 2) * 16 : 0);
+  s.off_misc = s.off_out + SL * (2 * NV) * 16;
   s.off_misc = (s.off_misc + 15) / 16 * 16;
   s.total = s.off_misc + 1024;
   return s;
@@ -180,17 +192,17 @@ __host__ __device__ inline bool channel_groups(int C2, int Kp, int SL, int nslot
   return false;
 }
 
-// Backward pass: a group holds FB filters x 3 kinds (y, dy/dmu, dy/dsigma) x (re, im) = 6*FB channels.
+// Training forward: a group holds FB filters x 3 kinds (y, dy/dmu, dy/dsigma) x (re, im) = 6*FB channels.
 // Channel of (filter fl in group, kind, ri):  half = fl / (FB/2);  c = half*(3*FB) + kind*FB + (fl % (FB/2))*2 + ri,
-// so each epilogue half (columns [half*3FB, (half+1)*3FB)) sees kind-major blocks of FB columns.
-__host__ __device__ inline int bwd_channel(int FB, int fl, int kind, int ri) {
+// so each epilogue half (columns [half*3FB, (half+1)*3FB), one CTA's bank rows) sees kind-major blocks of FB columns.
+__host__ __device__ inline int train_channel(int FB, int fl, int kind, int ri) {
   const int hf = FB / 2;
   return (fl / hf) * (3 * FB) + kind * FB + (fl % hf) * 2 + ri;
 }
-// filters per backward group: 16 (CG = 96) when the plan fits, else 8 (CG = 48); 0 = unsupported
-__host__ __device__ inline int bwd_filters_per_group(int Kp, int nslot) {
-  if (nslot <= 3 && smem_plan(96, Kp, 0, 1).total <= SMEM_LIMIT) return 16;
-  if (nslot <= 5 && smem_plan(48, Kp, 0, 1).total <= SMEM_LIMIT) return 8;
+// filters per training group: 16 (CG = 96) when the plan fits, else 8 (CG = 48); 0 = unsupported
+__host__ __device__ inline int train_filters_per_group(int Kp, int SL, int nslot) {
+  if (nslot <= 3 && smem_plan(96, Kp, SL, 1, 3).total <= SMEM_LIMIT) return 16;
+  if (nslot <= 5 && smem_plan(48, Kp, SL, 1, 5).total <= SMEM_LIMIT) return 8;
   return 0;
 }
 

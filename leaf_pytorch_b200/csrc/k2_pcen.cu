@@ -14,6 +14,7 @@
 // only HBM-bound stage of the path (~14 B per output element).
 #include "leafk_common.cuh"
 #include "k2_pcen_args.cuh"
+#include <cuda_bf16.h>
 #include <cstring>
 
 namespace leafk {
@@ -37,7 +38,8 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
   const int rows = g.B * g.F;
   const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;       // clip length <= 2^30 (checked on the host)
   const int n_end = g.n_begin + g.n_count;
-  const size_t tile_stride = (size_t)g.F * g.SL;
+  const int FV = a.q_out != nullptr ? 4 * g.F : g.F;            // virtual filters per (clip, tile) block
+  const size_t tile_stride = (size_t)FV * g.SL;
 
   for (int row = blockIdx.x * K2_WARPS + warp; row < rows; row += gridDim.x * K2_WARPS) {
     const int b = row / g.F, f = row - b * g.F;
@@ -45,16 +47,27 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
       if (lane == 0) {
         const int* flag = a.done + b;
         int v;
-        unsigned spins = 0;
-        do {
-          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-          if (v < a.done_target) { __nanosleep(100); if (++spins > (1u << 25)) __trap(); }   // bounded: a bug must not hang the GPU
-        } while (v < a.done_target);
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v < a.done_target) {
+          const long long t0 = global_timer_ns();
+          do {
+            __nanosleep(100);
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            // bounded (K1 itself may be waiting up to H2D_TIMEOUT_NS for a host copy): report instead of hanging or
+            // killing the context; the host API returns the error word after its next synchronisation
+            if (v < a.done_target && global_timer_ns() - t0 > 2 * H2D_TIMEOUT_NS) {
+              if (a.err != nullptr) atomicExch(a.err, LEAFK_ASYNC_K1_TIMEOUT);
+              break;
+            }
+          } while (v < a.done_target);
+        }
       }
       __syncwarp();
     }
     const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + (size_t)f * g.SL;
-    float* orow = a.out + (size_t)b * a.ldo_b + (size_t)f * a.ldo_f;
+    const size_t ooff = (size_t)b * a.ldo_b + (size_t)f * a.ldo_f;
+    float* orow = a.out + ooff;
+    __nv_bfloat16* orow16 = reinterpret_cast<__nv_bfloat16*>(a.out) + ooff;
     float* prow = a.saved_p ? a.saved_p + (size_t)b * a.ldo_b + (size_t)f * a.ldo_f : nullptr;
 
     float w = 0.f, alpha = 1.f, delta = 0.f, q = 1.f, dq = 0.f, om = 1.f, bias = 0.f;
@@ -93,9 +106,9 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
         have_prm = true;
         bias = a.pool_b ? __ldg(a.pool_b + f) : 0.f;
         if (a.compression) {
-          w = fminf(fmaxf(__ldg(a.ema_w + f), 0.f), 1.f);          // postprocessing.py:14
-          alpha = fminf(__ldg(a.alpha + f), 1.0f);                 // postprocessing.py:63
-          q = 1.0f / fmaxf(__ldg(a.root + f), 1.0f);               // postprocessing.py:64-65
+          w = clamp_nan(__ldg(a.ema_w + f), 0.f, 1.f);             // postprocessing.py:14 (NaN propagates like torch.clamp)
+          alpha = min_nan(__ldg(a.alpha + f), 1.0f);               // postprocessing.py:63
+          q = 1.0f / max_nan(__ldg(a.root + f), 1.0f);             // postprocessing.py:64-65
           delta = __ldg(a.delta + f);
           dq = pow_pos(delta, q);
           om = 1.0f - w;
@@ -106,7 +119,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) p[u] = fmaxf(p[u] + bias, a.clamp_min);   // pooling.py:41, frontend.py:84
+      for (int u = 0; u < 4; ++u) p[u] = max_nan(p[u] + bias, a.clamp_min);  // pooling.py:41, frontend.py:84 (torch.maximum keeps NaN)
       float o[4] = {p[0], p[1], p[2], p[3]};
       if (a.compression) {
         if (!have_carry) {                                    // smoother starts at the first frame
@@ -137,8 +150,35 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
       for (int u = 0; u < 4; ++u) {
         const int n = n0 + 32 * u + lane;
         if (ok[u]) {
-          orow[n - g.n_begin] = o[u];
+          if (a.out_bf16) orow16[n - g.n_begin] = __float2bfloat16_rn(o[u]);
+          else orow[n - g.n_begin] = o[u];
           if (prow) prow[n - g.n_begin] = p[u];
+        }
+      }
+      if (a.q_out != nullptr) {
+        // training forward: the pooled bilinear forms of the parameter gradients, assembled like p (tile order)
+        const size_t qstride = (size_t)g.B * g.F * g.n_count;
+        float* qrow = a.q_out + ((size_t)b * g.F + f) * g.n_count;
+#pragma unroll 1
+        for (int kind = 1; kind < 4; ++kind) {
+          const float* qbase = pbase + (size_t)kind * g.F * g.SL;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int n = n0 + 32 * u + lane;
+            if (!ok[u]) continue;
+            int wlo = n * g.H - g.padL, whi = wlo + g.K - 1;
+            if (wlo < te_lo) wlo = te_lo;
+            if (whi > te_hi - 1) whi = te_hi - 1;
+            const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
+            float s = 0.f;
+            for (int i = i0; i <= i1; ++i) {
+              const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
+              int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
+              if (nf < g.n_begin) nf = g.n_begin;
+              s += __ldcg(qbase + (size_t)i * tile_stride + (n - nf));
+            }
+            qrow[(size_t)(kind - 1) * qstride + (n - g.n_begin)] = s;
+          }
         }
       }
     }

@@ -22,11 +22,19 @@ constexpr int F32_TILE = 512;
 bool k1_tc_supported(const Geom& g, const char** why);
 cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, const float* cprm,
                          float* ppart, int tc_cg, int tc_groups, const int* tc_perm, const int* tc_zones, int* done,
-                         cudaStream_t stream, const int* ready, int clips_per_flag, long long* perf);
+                         cudaStream_t stream, const int* ready, int clips_per_flag, long long* perf, int* err_word);
 constexpr int TC_TILE = 1024;
 // k2_pcen.cu
 cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cudaStream_t stream);
 // bwd.cu
+int train_supported(int F, int K, int H);
+size_t train_workspace_bytes(const leafk_config* cfg, int B, int T);
+int forward_train_run(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T, float* out,
+                      float* saved, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t backward_saved_workspace_bytes(const leafk_config* cfg, int B, int T, int want_grad_x);
+int backward_saved_run(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
+                       const float* grad_out, const float* saved, const leafk_grads* grads, float* grad_x,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t bwd_workspace_bytes(const leafk_config* cfg, int B, int T);
 int bwd_run(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
             const float* grad_out, const float* saved_p, const leafk_grads* grads, float* grad_x,
@@ -74,6 +82,8 @@ static int make_geom(const leafk_config* cfg, int B, long long ldx, long long T_
   if (cfg->F < 1 || cfg->K < 2 || cfg->H < 1) return fail(LEAFK_EINVAL, "bad F/K/H (%d,%d,%d)", cfg->F, cfg->K, cfg->H);
   if (cfg->input_format != LEAFK_INPUT_F32 && cfg->input_format != LEAFK_INPUT_S16)
     return fail(LEAFK_EINVAL, "unknown input_format %d", cfg->input_format);
+  if (cfg->output_format != LEAFK_OUTPUT_F32 && cfg->output_format != LEAFK_OUTPUT_BF16)
+    return fail(LEAFK_EINVAL, "unknown output_format %d", cfg->output_format);
   if (B < 1 || T_total < 1 || T_win < 1) return fail(LEAFK_EINVAL, "bad B/T (%d,%lld,%d)", B, T_total, T_win);
   if (T_total > (1LL << 30)) return fail(LEAFK_EINVAL, "clip too long (%lld samples)", T_total);
   Geom g;
@@ -112,6 +122,9 @@ static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace
   const int sl_tc = (TC_TILE + g.K - 2) / g.H + 1;
   tc::channel_groups(g.C2, g.Kp, sl_tc, tc::slots_per_thread(g.K, g.H), tc_groups, tc_cg);
   size_t off = 0;
+  // first, so that its address does not depend on the shapes: 16 ints (int 0 = asynchronous error word), then the
+  // per-clip completion counters
+  w->off_done = off;  off += align256(sizeof(int) * ((size_t)g.B + 16));
   w->off_cprm = off; off += align256(sizeof(float) * 8 * g.F);
   w->off_w32 = off;  off += align256(sizeof(float) * (size_t)g.Kp * g.C2p);
   w->off_g32 = off;  off += align256(sizeof(float) * (size_t)g.K * g.F);
@@ -122,7 +135,6 @@ static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace
   size_t a = (size_t)max_tiles_fp32 * sl32, b = (size_t)max_tiles_tc * sltc;
   off += align256(sizeof(float) * (size_t)g.B * g.F * (a > b ? a : b));
   w->off_flags = off; off += 256;                      // 32 slice-ready flags (leafk_forward_host) + 2 perf counters
-  w->off_done = off;  off += align256(sizeof(int) * (size_t)g.B);
   w->total = off;
 }
 
@@ -204,18 +216,19 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   int* tc_zones = tc_perm + (size_t)tc_groups * (tc_cg / 2);
   const float prune_c = (cfg->algo & LEAFK_TC_NOPRUNE) ? 0.f : tc::PRUNE_C;
   const float prune_c3 = (cfg->algo & LEAFK_TC_NOPRUNE) ? 0.f : tc::PRUNE_C3;
-  int* done = (int*)(base + w.off_done);
+  int* err_word = (int*)(base + w.off_done);
+  int* done = err_word + 16;
 
   prof_mark(0, stream);
   cudaError_t err;
   if (cfg->algo & LEAFK_REUSE_BANKS) {
     // banks, sort and schedule are still in the workspace (same parameters): only the per-clip counters are reset
-    err = (algo == LEAFK_ALGO_TC) ? cudaMemsetAsync(done, 0, sizeof(int) * (size_t)g.B, stream) : cudaSuccess;
+    err = cudaMemsetAsync(err_word, 0, sizeof(int) * ((size_t)g.B + 16), stream);
     if (err != cudaSuccess) return fail(LEAFK_ECUDA, "counter reset: %s", cudaGetErrorString(err));
   } else {
     launch_k0(prm->kernel, prm->pool_w, g.F, g.K, g.Kp, g.C2p, cprm, w32, g32,
               algo == LEAFK_ALGO_TC ? w16 : nullptr, tc_cg, tc_groups, tc_perm, tc_zones, prune_c, prune_c3,
-              algo == LEAFK_ALGO_TC ? done : nullptr, g.B, stream);
+              err_word, g.B + 16, stream);             // also zeroes the error word and the per-clip counters
     err = cudaGetLastError();
     if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0 launch: %s", cudaGetErrorString(err));
   }
@@ -225,12 +238,16 @@ static int forward_impl(const leafk_config* cfg, const leafk_params* prm, const 
   if (algo_out) *algo_out = algo;
   if (algo == LEAFK_ALGO_TC)
     err = launch_k1_tc(g, x_win, w16, cprm, ppart, tc_cg, tc_groups, tc_perm, tc_zones, done, stream,
-                       clips_per_flag > 0 ? flags : nullptr, clips_per_flag, g_prof_on ? (long long*)(flags + 32) : nullptr);
+                       clips_per_flag > 0 ? flags : nullptr, clips_per_flag, g_prof_on ? (long long*)(flags + 32) : nullptr,
+                       err_word);
   else
     err = launch_k1_fp32(g, x_win, w32, g32, ppart, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k1 launch: %s", cudaGetErrorString(err));
   prof_mark(2, stream);
   PcenArgs a;
+  memset(&a, 0, sizeof(a));
+  a.err = err_word;
+  a.out_bf16 = cfg->output_format == LEAFK_OUTPUT_BF16 ? 1 : 0;
   a.pool_b = prm->pool_b; a.alpha = prm->alpha; a.delta = prm->delta; a.root = prm->root;
   a.ema_w = prm->ema_w; a.ema_in = ema_state_in; a.ema_out = ema_state_out; a.out = out;
   a.saved_p = saved_p; a.ldo_b = ldo_b; a.ldo_f = ldo_f; a.pcen_floor = cfg->pcen_floor;
@@ -457,6 +474,36 @@ int leafk_forward_host_async(const leafk_config* cfg, const leafk_params* prm, c
 }
 
 size_t leafk_backward_workspace_bytes(const leafk_config* cfg, int B, int T) { return bwd_workspace_bytes(cfg, B, T); }
+
+int leafk_train_supported(int F, int K, int H) { return train_supported(F, K, H); }
+size_t leafk_train_workspace_bytes(const leafk_config* cfg, int B, int T) { return train_workspace_bytes(cfg, B, T); }
+int leafk_forward_train(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T, float* out,
+                        float* saved, void* workspace, size_t workspace_bytes, void* stream) {
+  if (cfg && cfg->output_format != LEAFK_OUTPUT_F32) return fail(LEAFK_EINVAL, "the training forward emits float32 features");
+  return forward_train_run(cfg, prm, x, B, T, out, saved, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+size_t leafk_backward_saved_workspace_bytes(const leafk_config* cfg, int B, int T, int want_grad_x) {
+  return backward_saved_workspace_bytes(cfg, B, T, want_grad_x);
+}
+int leafk_backward_saved(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
+                         const float* grad_out, const float* saved, const leafk_grads* grads, float* grad_x,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  return backward_saved_run(cfg, prm, x, B, T, grad_out, saved, grads, grad_x, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+}
+
+int leafk_async_status(const void* workspace) {
+  if (!workspace) return fail(LEAFK_EINVAL, "null pointer argument");
+  int word = 0;
+  cudaError_t e = cudaMemcpy(&word, workspace, sizeof(int), cudaMemcpyDeviceToHost);   // synchronous by design
+  if (e != cudaSuccess) return fail(LEAFK_ECUDA, "status read: %s", cudaGetErrorString(e));
+  if (word == LEAFK_ASYNC_H2D_TIMEOUT)
+    return fail(LEAFK_ETIMEOUT, "a slice of the host-to-device copy never signalled ready (stalled copy); features invalid");
+  if (word == LEAFK_ASYNC_K1_TIMEOUT)
+    return fail(LEAFK_ETIMEOUT, "the PCEN kernel gave up waiting for the Gabor kernel's per-clip counters; features invalid");
+  if (word != 0) return fail(LEAFK_ECUDA, "unknown asynchronous error word %d", word);
+  return LEAFK_OK;
+}
 
 int leafk_backward(const leafk_config* cfg, const leafk_params* prm, const float* x, int B, int T,
                    const float* grad_out, const float* saved_p, const leafk_grads* grads, float* grad_x,

@@ -85,6 +85,23 @@ struct Workspace {
 // per-filter constants produced by k0 (float[8] per filter)
 enum { CP_MU = 0, CP_SIGMA = 1, CP_NORM = 2, CP_INV2S2 = 3, CP_POOLS = 4, CP_POOLA = 5, CP_WSCALE = 6, CP_PAD = 7 };
 
+// asynchronous error codes (error word in the workspace, read back by leafk_async_status)
+constexpr int LEAFK_ASYNC_H2D_TIMEOUT = 1;      // a slice-ready flag of the host-pipelined forward never arrived
+constexpr int LEAFK_ASYNC_K1_TIMEOUT = 2;       // K2 gave up waiting for K1's per-clip completion counter
+constexpr long long H2D_TIMEOUT_NS = 10LL * 1000 * 1000 * 1000;
+#ifdef __CUDACC__
+// torch.clamp / torch.minimum / torch.maximum propagate NaN (fminf / fmaxf drop it): a NaN parameter or waveform must
+// come out as NaN features like in the reference, not as a silently clamped value
+__device__ __forceinline__ float clamp_nan(float v, float lo, float hi) { return (v != v) ? v : fminf(fmaxf(v, lo), hi); }
+__device__ __forceinline__ float max_nan(float v, float c) { return (v != v) ? v : fmaxf(v, c); }
+__device__ __forceinline__ float min_nan(float v, float c) { return (v != v) ? v : fminf(v, c); }
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace leafk

@@ -134,6 +134,26 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
                : "memory");
 }
 
+// ---------------------------------------------------------------- register reallocation between warpgroups
+// The CTA launches with the same register count for every warp; a warpgroup (4 consecutive warps) that needs few
+// gives some back and the others take them.  All warps of the warpgroup must execute the instruction.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// ---------------------------------------------------------------- bulk copy (TMA, 1-D) global -> shared
+// One thread: expect `bytes` on the CTA-local mbarrier, then start the copy; the data arrives through the async
+// proxy (the proxy tcgen05.mma reads operands through) and the barrier completes when all bytes have landed.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -220,6 +240,22 @@ __device__ __forceinline__ void tmem_ld8x2_sync(uint32_t taddr_a, uint32_t taddr
       : "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) { va[i] = __uint_as_float(a[i]); vb[i] = __uint_as_float(b[i]); }
+}
+// three 8-column loads (y, z, v accumulators of 4 filters), one wait
+__device__ __forceinline__ void tmem_ld8x3_sync(uint32_t ta, uint32_t tb, uint32_t tc_, float* va, float* vb, float* vc) {
+  uint32_t a[8], b[8], c[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%25];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [%26];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(b[0]),
+        "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(c[0]), "=r"(c[1]),
+        "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7])
+      : "r"(ta), "r"(tb), "r"(tc_)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { va[i] = __uint_as_float(a[i]); vb[i] = __uint_as_float(b[i]); vc[i] = __uint_as_float(c[i]); }
 }
 // two 16-column loads from two addresses (main / correction accumulators), one wait
 __device__ __forceinline__ void tmem_ld16x2_sync(uint32_t taddr_a, uint32_t taddr_b, float* va, float* vb) {

@@ -136,15 +136,17 @@ class Leaf(nn.Module):
     """LEAF frontend: (B,1,T) float32 waveform on a B200 -> (B,n_filters,N) features.
 
     Same signature as the reference (frontend.py:23-36).  Extra keyword ``algo`` selects the
-    correlation kernel: "auto" (tensor cores when the geometry allows), "tc", or "fp32";
-    ``fast_backward=True`` trades gradient accuracy (~1e-6 -> ~5e-4 of max|g| on small batches) for 27 % less
-    backward time by dropping one of the three split products (see LEAFK_BWD_2PRODUCT in include/leafk.h).
+    correlation kernel: "auto" (tensor cores when the geometry allows), "tc", "tc_full" (no support pruning) or
+    "fp32".  ``out_dtype=torch.bfloat16`` makes the PCEN kernel write bf16 features (inference only) and
+    ``out_layout="b1fn"`` returns them as (B,1,F,N), the shape the reference's Classifier feeds its 2-D backbone
+    (reference models/classifier.py:15-17) -- a view, no copy.
     """
 
     def __init__(self, n_filters: int = 40, sample_rate: int = 16000, window_len: float = 25.,
                  window_stride: float = 10., preemp: bool = False, init_min_freq=60.0, init_max_freq=7800.0,
                  mean_var_norm: bool = False, pcen_compression: bool = True, use_legacy_complex=False,
-                 initializer="default", algo: str = "auto", fast_backward: bool = False):
+                 initializer="default", algo: str = "auto", out_dtype: torch.dtype = torch.float32,
+                 out_layout: str = "bfn"):
         super().__init__()
         window_size = int(sample_rate * window_len // 1000 + 1)
         hop = int(sample_rate * window_stride // 1000)
@@ -167,16 +169,19 @@ class Leaf(nn.Module):
         else:
             self._compression = None
         self._maximum_val = torch.tensor(1e-5)
+        if out_layout not in ("bfn", "b1fn"):
+            raise ValueError("out_layout must be 'bfn' (reference) or 'b1fn'")
         self.algo = algo
-        self.fast_backward = fast_backward
+        self.out_dtype = out_dtype
+        self.out_layout = out_layout
         self._spec = LF.LeafSpec(F=n_filters, K=window_size, H=hop, compression=bool(pcen_compression), algo=algo,
-                                 pcen_floor=1e-12, clamp_min=1e-5, fast_backward=fast_backward)
+                                 pcen_floor=1e-12, clamp_min=1e-5, out_dtype=out_dtype)
 
     # ------------------------------------------------------------------ helpers
     @property
     def spec(self) -> LF.LeafSpec:
-        if self._spec.algo != self.algo or self._spec.fast_backward != self.fast_backward:
-            self._spec = LF.LeafSpec(**{**self._spec.__dict__, "algo": self.algo, "fast_backward": self.fast_backward})
+        if self._spec.algo != self.algo or self._spec.out_dtype != self.out_dtype:
+            self._spec = LF.LeafSpec(**{**self._spec.__dict__, "algo": self.algo, "out_dtype": self.out_dtype})
         return self._spec
 
     def num_frames(self, n_samples: int) -> int:
@@ -193,8 +198,10 @@ class Leaf(nn.Module):
         """reference frontend.py:78-89, fused."""
         if isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 3 and x.shape[0] == 0 and x.shape[2] > 0:
             # empty batch: the reference returns an empty (0,F,N) tensor (conv1d accepts B = 0)
-            return torch.zeros((0, self.spec.F, self.spec.num_frames(x.shape[2])), dtype=torch.float32, device=x.device)
-        return LF.leaf_forward(self.spec, x, *self._param_tuple())
+            out = torch.zeros((0, self.spec.F, self.spec.num_frames(x.shape[2])), dtype=self.out_dtype, device=x.device)
+        else:
+            out = LF.leaf_forward(self.spec, x, *self._param_tuple())
+        return out.unsqueeze(1) if self.out_layout == "b1fn" else out
 
     def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
                      n_slices: int = 8) -> torch.Tensor:

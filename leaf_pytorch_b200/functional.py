@@ -2,11 +2,17 @@
 
 ``leaf_forward`` is what ``Leaf.forward`` (frontend.py here, reference frontend.py:78-89) calls;
 it is differentiable with respect to the seven frontend parameters (reference train.py:258 only
-ever needs those) and, optionally, the waveform.
+ever needs those) and the waveform.
+
+Training (parameters require grad and autograd is recording): on geometries the tensor-core training kernel covers
+the forward is ``leafk_forward_train``, which also pools the bilinear forms the parameter gradients need, and the
+backward (``leafk_backward_saved``) runs no correlation; other geometries use ``leafk_forward`` + the generic FP32
+``leafk_backward``.  Under ``torch.no_grad()`` the plain forward runs and nothing is saved.
 """
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -28,12 +34,15 @@ class LeafSpec:
     algo: str = "auto"
     pcen_floor: float = PCEN_FLOOR
     clamp_min: float = CLAMP_MIN
-    fast_backward: bool = False      # LEAFK_BWD_2PRODUCT: drop the x_lo*W_hi product in the backward correlations
+    out_dtype: torch.dtype = torch.float32    # torch.bfloat16: K2 writes bf16 features (inference; LEAFK_OUTPUT_BF16)
 
-    def config(self, input_dtype=torch.float32, reuse_banks: bool = False) -> N.Config:
-        algo = N.ALGOS[self.algo] | (N.BWD_2PRODUCT if self.fast_backward else 0) | (N.REUSE_BANKS if reuse_banks else 0)
+    def config(self, input_dtype=torch.float32, reuse_banks: bool = False, out_dtype=None) -> N.Config:
+        algo = N.ALGOS[self.algo] | (N.REUSE_BANKS if reuse_banks else 0)
+        out_dtype = self.out_dtype if out_dtype is None else out_dtype
+        if out_dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"out_dtype must be float32 or bfloat16, got {out_dtype}")
         return N.Config(self.F, self.K, self.H, self.pcen_floor, self.clamp_min, int(self.compression),
-                        algo, 1 if input_dtype == torch.int16 else 0)
+                        algo, 1 if input_dtype == torch.int16 else 0, 1 if out_dtype == torch.bfloat16 else 0)
 
     def num_frames(self, T: int) -> int:
         lo = self.K // 2 + self.K % 2 - 1
@@ -98,13 +107,39 @@ def forward_raw(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, e
     cfg = spec.config(x.dtype)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
     with torch.cuda.device(x.device):
-        out = torch.empty((B, spec.F, n), dtype=torch.float32, device=x.device)
-        saved = torch.empty_like(out) if save_p else None
+        out = torch.empty((B, spec.F, n), dtype=spec.out_dtype, device=x.device)
+        saved = torch.empty((B, spec.F, n), dtype=torch.float32, device=x.device) if save_p else None
         ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         rc = L.leafk_forward(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(out), _ptr(saved), _ptr(ws),
                              ws_bytes, _stream_ptr(x.device))
     N.check(rc, "leafk_forward")
+    del keep
+    return out, saved
+
+
+def train_supported(spec: LeafSpec) -> bool:
+    """True when the tensor-core training kernel covers this geometry (else training uses the generic FP32 backward)."""
+    return spec.algo != "fp32" and bool(N.lib().leafk_train_supported(spec.F, spec.K, spec.H))
+
+
+def forward_train_raw(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w):
+    """Training forward on the current stream; no autograd.  Returns (out (B,F,N), saved (4,B,F,N)):
+    saved[0] = floored pooled energies, saved[1:4] = pooled bilinear forms of the parameter gradients."""
+    L = N.lib()
+    x = _check_input(x)
+    B, _, T = x.shape
+    n = spec.num_frames(T)
+    cfg = spec.config(x.dtype, out_dtype=torch.float32)
+    prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
+    with torch.cuda.device(x.device):
+        out = torch.empty((B, spec.F, n), dtype=torch.float32, device=x.device)
+        saved = torch.empty((4, B, spec.F, n), dtype=torch.float32, device=x.device)
+        ws_bytes = L.leafk_train_workspace_bytes(C.byref(cfg), B, T)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=x.device)
+        rc = L.leafk_forward_train(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(out), _ptr(saved), _ptr(ws),
+                                   ws_bytes, _stream_ptr(x.device))
+    N.check(rc, "leafk_forward_train")
     del keep
     return out, saved
 
@@ -165,20 +200,28 @@ def forward_window(spec: LeafSpec, x_win, T_total: int, t_off: int, n_begin: int
 
 
 class _LeafFunction(torch.autograd.Function):
-    """autograd node: forward = leafk_forward, backward = leafk_backward (parameter gradients of
-    reference frontend.py:78-89; input gradient only when the waveform requires grad)."""
+    """autograd node of reference frontend.py:78-89.  forward = leafk_forward_train (tensor-core geometries) or
+    leafk_forward; backward = leafk_backward_saved or the generic leafk_backward; the gradient w.r.t. the waveform is
+    computed only when the waveform requires grad."""
 
     @staticmethod
     def forward(ctx, spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w):
-        need_grad = any(t is not None and t.requires_grad for t in (x, kernel, pool_w, pool_b, alpha, delta, root, ema_w))
-        out, saved = forward_raw(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w, save_p=need_grad)
+        if spec.out_dtype != torch.float32:
+            raise TypeError("training needs float32 features (out_dtype=torch.bfloat16 is an inference option)")
         ctx.spec = spec
         ctx.has_bias = pool_b is not None
         ctx.has_pcen = alpha is not None
-        tensors = [x, saved, kernel, pool_w] + ([pool_b] if ctx.has_bias else []) + \
+        ctx.fused = train_supported(spec)
+        if ctx.fused:
+            out, saved = forward_train_raw(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w)
+        else:
+            out, saved = forward_raw(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w, save_p=True)
+        # the waveform is needed again only by the generic backward and for its own gradient
+        ctx.keep_x = (not ctx.fused) or ctx.needs_input_grad[1]
+        tensors = [x if ctx.keep_x else None, saved, kernel, pool_w] + ([pool_b] if ctx.has_bias else []) + \
                   ([alpha, delta, root, ema_w] if ctx.has_pcen else [])
-        if need_grad:
-            ctx.save_for_backward(*tensors)
+        ctx.save_for_backward(*tensors)
+        ctx.x_shape, ctx.x_dtype = tuple(x.shape), x.dtype
         return out
 
     @staticmethod
@@ -196,23 +239,35 @@ class _LeafFunction(torch.autograd.Function):
         alpha = delta = root = ema_w = None
         if ctx.has_pcen:
             alpha, delta, root, ema_w = saved[idx:idx + 4]
-        x = _check_input(x)
-        B, _, T = x.shape
-        cfg = spec.config(x.dtype)
-        prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
+        B, _, T = ctx.x_shape
+        if x is not None:
+            x = _check_input(x)
+        cfg = spec.config(ctx.x_dtype, out_dtype=torch.float32)
+        dev = p.device
+        prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, dev)
         grad_out = grad_out.contiguous().to(torch.float32)
-        dev = x.device
+        want_gx = ctx.needs_input_grad[1]
+        if want_gx and ctx.x_dtype != torch.float32:
+            raise TypeError("no gradient with respect to an int16 waveform")
         with torch.cuda.device(dev):
-            def z(t):                                    # leafk_backward writes (does not accumulate) every entry
+            def z(t):                                    # the backward writes (does not accumulate) every entry
                 return None if t is None else torch.empty(t.numel(), dtype=torch.float32, device=dev)
             g = [z(kernel), z(pool_w), z(pool_b), z(alpha), z(delta), z(root), z(ema_w)]
             grads = N.Grads(*[None if t is None else t.data_ptr() for t in g])
-            gx = torch.empty(x.shape, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
-            ws_bytes = L.leafk_backward_workspace_bytes(C.byref(cfg), B, T)
-            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-            rc = L.leafk_backward(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(grad_out), _ptr(p),
-                                  C.byref(grads), _ptr(gx), _ptr(ws), ws_bytes, _stream_ptr(dev))
-        N.check(rc, "leafk_backward")
+            gx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dev) if want_gx else None
+            if ctx.fused:
+                ws_bytes = L.leafk_backward_saved_workspace_bytes(C.byref(cfg), B, T, int(want_gx))
+                ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+                rc = L.leafk_backward_saved(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(grad_out), _ptr(p),
+                                            C.byref(grads), _ptr(gx), _ptr(ws), ws_bytes, _stream_ptr(dev))
+                what = "leafk_backward_saved"
+            else:
+                ws_bytes = L.leafk_backward_workspace_bytes(C.byref(cfg), B, T)
+                ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+                rc = L.leafk_backward(C.byref(cfg), C.byref(prm), _ptr(x), B, T, _ptr(grad_out), _ptr(p),
+                                      C.byref(grads), _ptr(gx), _ptr(ws), ws_bytes, _stream_ptr(dev))
+                what = "leafk_backward"
+        N.check(rc, what)
         del keep
 
         def shaped(gt, like):
@@ -226,10 +281,16 @@ def leaf_forward(spec: LeafSpec, x, kernel, pool_w, pool_b=None, alpha=None, del
     """Differentiable fused LEAF forward: (B,1,T) float32 CUDA waveform -> (B,F,N)."""
     if spec.compression and any(t is None for t in (alpha, delta, root, ema_w)):
         raise ValueError("compression=True needs alpha, delta, root and ema_w")
+    tensors = (x, kernel, pool_w, pool_b, alpha, delta, root, ema_w)
+    if not torch.is_grad_enabled() or not any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        # inference: nothing is saved for a backward that will not come
+        return forward_raw(spec, x, *[None if t is None else t.detach() for t in tensors[1:]])[0]
     return _LeafFunction.apply(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w)
 
 
-_host_cache = {}
+_host_cache = {}                 # (device, shapes, geometry, algo, dtype) -> device scratch of forward_host
+_host_cache_lock = threading.Lock()
+_HOST_CACHE_MAX = 8
 
 
 def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, alpha, delta, root, ema_w,
@@ -249,7 +310,7 @@ def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, a
     x_host = x_host.contiguous()
     B, _, T = x_host.shape
     n = spec.num_frames(T)
-    cfg = spec.config(x_host.dtype)
+    cfg = spec.config(x_host.dtype, out_dtype=torch.float32)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, device)
     if out_host is None:
         out_host = torch.empty((B, spec.F, n), dtype=torch.float32, pin_memory=True)
@@ -257,15 +318,17 @@ def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, a
             or not out_host.is_contiguous():
         raise ValueError("out_host must be a contiguous float32 CPU tensor of shape (B,F,N)")
     with torch.cuda.device(device):
-        key = (device.index, B, T, spec.F, n, x_host.dtype)
-        bufs = _host_cache.get(key)
-        if bufs is None:
-            _host_cache.clear()
-            ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n)
-            bufs = (torch.empty(B * T, dtype=x_host.dtype, device=device),
-                    torch.empty(B * spec.F * n, dtype=torch.float32, device=device),
-                    torch.empty(ws_bytes, dtype=torch.uint8, device=device), torch.cuda.Stream(device=device))
-            _host_cache[key] = bufs
+        ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n)
+        key = (device.index, B, T, spec.F, spec.K, spec.H, spec.algo, n, x_host.dtype)
+        with _host_cache_lock:
+            bufs = _host_cache.get(key)
+            if bufs is None or bufs[2].numel() < ws_bytes:
+                while len(_host_cache) >= _HOST_CACHE_MAX:          # bounded: drop the oldest shape, keep the rest
+                    _host_cache.pop(next(iter(_host_cache)))
+                bufs = (torch.empty(B * T, dtype=x_host.dtype, device=device),
+                        torch.empty(B * spec.F * n, dtype=torch.float32, device=device),
+                        torch.empty(ws_bytes, dtype=torch.uint8, device=device), torch.cuda.Stream(device=device))
+                _host_cache[key] = bufs
         dev_x, dev_out, ws, side = bufs
         cur = torch.cuda.current_stream(device)
         side.wait_stream(cur)
@@ -274,6 +337,8 @@ def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, a
                                   _ptr(ws), ws.numel(), C.c_void_p(cur.cuda_stream), C.c_void_p(side.cuda_stream))
         N.check(rc, "leafk_forward_host")
         cur.synchronize()
+        # a stalled H2D slice is reported here instead of trapping inside the kernel
+        N.check(L.leafk_async_status(_ptr(ws)), "leafk_forward_host")
     del keep
     return out_host
 

@@ -23,7 +23,7 @@ from . import functional as LF
 
 
 class _Set:
-    __slots__ = ("dev_x", "dev_out", "ws", "ev_compute", "ev_out", "out_host", "busy", "keep")
+    __slots__ = ("dev_x", "dev_out", "ws", "ev_compute", "ev_out", "out_host", "busy", "keep", "ticket")
 
 
 class HostPipeline:
@@ -57,19 +57,24 @@ class HostPipeline:
                 s.ev_out = self.lib.leafk_event_create()
                 if not s.ev_compute or not s.ev_out:
                     raise N.LeafNativeError("could not create CUDA events")
-                s.out_host, s.busy, s.keep = None, False, None
+                s.out_host, s.busy, s.keep, s.ticket = None, False, None, -1
                 self.sets.append(s)
-        self._next = 0
+        self._next = 0                    # monotonically increasing ticket of the next batch
+        self._done = {}                   # ticket -> features of batches collected early (their set was needed again)
 
     def submit(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None) -> int:
-        """Enqueue one batch; returns a ticket for ``result``.  Never blocks unless every set is in flight."""
+        """Enqueue one batch; returns a ticket for ``result`` (tickets never repeat).  Blocks only when every buffer
+        set is in flight; the batch that has to make room is collected and kept until its ticket is asked for."""
         if x_host.is_cuda or x_host.dtype != self.dtype or tuple(x_host.shape) != (self.B, 1, self.T):
             raise ValueError(f"x_host must be a CPU {self.dtype} tensor of shape {(self.B, 1, self.T)}")
-        idx = self._next
-        self._next = (self._next + 1) % len(self.sets)
-        s = self.sets[idx]
+        ticket = self._next
+        self._next += 1
+        s = self.sets[ticket % len(self.sets)]
         if s.busy:
-            self.result(idx)                              # oldest batch not collected yet: wait for it
+            self._done[s.ticket] = self._collect(s)       # oldest batch not collected yet: wait for it, keep its result
+        # parameters may have been updated on the caller's stream (optimizer.step, load_state_dict, .to()): the
+        # pipeline's own streams must see those writes
+        self.compute_stream.wait_stream(torch.cuda.current_stream(self.device))
         if out_host is None:
             out_host = torch.empty((self.B, self.spec.F, self.n_frames), dtype=torch.float32, pin_memory=True)
         x_host = x_host.contiguous()
@@ -83,22 +88,30 @@ class HostPipeline:
                 C.c_void_p(self.compute_stream.cuda_stream), C.c_void_p(self.copy_stream.cuda_stream),
                 C.c_void_p(self.d2h_stream.cuda_stream), C.c_void_p(s.ev_compute), C.c_void_p(s.ev_out))
         N.check(rc, "leafk_forward_host_async")
-        s.out_host, s.busy, s.keep = out_host, True, (keep, x_host)
-        return idx
+        s.out_host, s.busy, s.keep, s.ticket = out_host, True, (keep, x_host), ticket
+        return ticket
 
-    def result(self, ticket: int) -> torch.Tensor:
-        """Block until the batch of ``ticket`` is on the host and return its (B,F,N) features."""
-        s = self.sets[ticket]
-        if not s.busy:
-            raise ValueError("no batch in flight for this ticket")
+    def _collect(self, s: _Set) -> torch.Tensor:
         N.check(self.lib.leafk_event_synchronize(C.c_void_p(s.ev_out)), "leafk_event_synchronize")
         s.busy, s.keep = False, None
+        # a stalled host-to-device slice is reported here (the kernels record it instead of trapping)
+        N.check(self.lib.leafk_async_status(C.c_void_p(s.ws.data_ptr())), "leafk_forward_host_async")
         return s.out_host
+
+    def result(self, ticket: int) -> torch.Tensor:
+        """Block until the batch of ``ticket`` is on the host and return its (B,F,N) features.  Each ticket can be
+        collected once; an unknown or already collected ticket raises."""
+        if ticket in self._done:
+            return self._done.pop(ticket)
+        s = self.sets[ticket % len(self.sets)] if 0 <= ticket < self._next else None
+        if s is None or not s.busy or s.ticket != ticket:
+            raise ValueError(f"no batch in flight for ticket {ticket}")
+        return self._collect(s)
 
     def close(self) -> None:
         for s in self.sets:
             if s.busy:
-                self.result(self.sets.index(s))
+                self._collect(s)
             if s.ev_compute:
                 self.lib.leafk_event_destroy(C.c_void_p(s.ev_compute)); s.ev_compute = None
             if s.ev_out:

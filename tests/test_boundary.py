@@ -242,12 +242,11 @@ def test_header_constants_match_the_python_binding():
     text = open(os.path.join(ROOT, "include", "leafk.h")).read()
     defs = {m.group(1): int(m.group(2).strip("()")) for m in re.finditer(r"#define\s+(LEAFK_\w+)\s+(\(?-?\d+\)?)", text)}
     assert defs["LEAFK_ALGO_AUTO"] == N.ALGO_AUTO and defs["LEAFK_ALGO_FP32"] == N.ALGO_FP32 and defs["LEAFK_ALGO_TC"] == N.ALGO_TC
-    assert defs["LEAFK_BWD_2PRODUCT"] == N.BWD_2PRODUCT
     assert defs["LEAFK_TC_NOPRUNE"] == N.TC_NOPRUNE
     assert defs["LEAFK_REUSE_BANKS"] == N.REUSE_BANKS
     assert N.ALGOS["tc_full"] == defs["LEAFK_ALGO_TC"] | defs["LEAFK_TC_NOPRUNE"]
-    flags = [defs["LEAFK_BWD_2PRODUCT"], defs["LEAFK_TC_NOPRUNE"], defs["LEAFK_REUSE_BANKS"]]
-    assert all(f > 15 and f & (f - 1) == 0 for f in flags) and len(set(flags)) == 3     # distinct bits above the kernel choice
+    flags = [defs["LEAFK_TC_NOPRUNE"], defs["LEAFK_REUSE_BANKS"]]
+    assert all(f > 15 and f & (f - 1) == 0 for f in flags) and len(set(flags)) == 2     # distinct bits above the kernel choice
     body = re.search(r"typedef struct leafk_config \{(.*?)\} leafk_config;", text, re.S).group(1)
     fields = re.findall(r"^\s*(?:int|float)\s+(\w+);", body, re.M)
     assert fields == [n for n, _ in N.Config._fields_]
@@ -266,5 +265,14 @@ def test_host_side_planning_calls_work_without_a_gpu():
     assert LF.tc_supported(40, 401, 160) and LF.tc_supported(80, 401, 160) and LF.tc_supported(8, 1601, 480)
     assert not LF.tc_supported(40, 401, 40)            # more than 5 frames per 8 samples: CUDA-core kernel
     assert spec.num_frames(16000) == 100 and spec.num_frames(15999) == 100 and spec.num_frames(16001) == 101
-    cfg = LF.LeafSpec(F=40, K=401, H=160, algo="tc_full", fast_backward=True).config(torch.int16, reuse_banks=True)
-    assert cfg.algo == N.ALGO_TC | N.TC_NOPRUNE | N.BWD_2PRODUCT | N.REUSE_BANKS and cfg.input_format == 1
+    cfg = LF.LeafSpec(F=40, K=401, H=160, algo="tc_full", out_dtype=torch.bfloat16).config(torch.int16, reuse_banks=True)
+    assert cfg.algo == N.ALGO_TC | N.TC_NOPRUNE | N.REUSE_BANKS and cfg.input_format == 1 and cfg.output_format == 1
+    # training path planning: the tensor-core training kernel covers the default and the 80-filter geometry, not hop 40
+    assert LF.train_supported(spec) and LF.train_supported(LF.LeafSpec(F=80, K=401, H=160))
+    assert not LF.train_supported(LF.LeafSpec(F=40, K=401, H=40)) and not LF.train_supported(LF.LeafSpec(F=40, K=401, H=160, algo="fp32"))
+    c = spec.config()
+    L = N.lib()
+    import ctypes as C
+    assert L.leafk_train_workspace_bytes(C.byref(c), 256, 16000) > 4 * 256 * 16 * 4 * 40 * 9
+    assert L.leafk_backward_saved_workspace_bytes(C.byref(c), 256, 16000, 1) > L.leafk_backward_saved_workspace_bytes(C.byref(c), 256, 16000, 0) > 0
+    assert L.leafk_backward_workspace_bytes(C.byref(c), 4, 16000) > 0
