@@ -32,6 +32,7 @@ namespace leafk {
 
 int fail(int code, const char* fmt, ...);
 void count_launch(int n);
+void prof_mark(int which, cudaStream_t stream);      // leafk_profile_begin/end: events around K0 / K1 / K2
 void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, int C2p, float* cprm,
                float* w32, float* g32, uint8_t* w16, int tc_cg, int tc_groups, int* tc_perm, int* tc_zones,
                float prune_c, float prune_c3, int* done, int n_done, cudaStream_t stream);
@@ -511,11 +512,14 @@ int forward_train_run(const leafk_config* cfg, const leafk_params* prm, const fl
   whole_clip_geom(cfg, B, T, tc::TILE, &g);
   const size_t bfn = (size_t)B * cfg->F * pl.N;
 
+  prof_mark(0, stream);
   launch_k0_train(prm->kernel, prm->pool_w, cfg->F, cfg->K, pl.Kp, pl.FB, pl.n_groups, tprm, w16t, err_word, B + 16, stream);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k0_train launch: %s", cudaGetErrorString(err));
+  prof_mark(1, stream);
   err = launch_k1_tc_train(g, x, w16t, pl.FB, pl.n_groups, tprm, ppart, done, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k1_tc_train launch: %s", cudaGetErrorString(err));
+  prof_mark(2, stream);
   PcenArgs a;
   memset(&a, 0, sizeof(a));
   a.pool_b = prm->pool_b; a.alpha = prm->alpha; a.delta = prm->delta; a.root = prm->root; a.ema_w = prm->ema_w;
@@ -525,6 +529,7 @@ int forward_train_run(const leafk_config* cfg, const leafk_params* prm, const fl
   a.q_out = saved + bfn;
   err = launch_k2(g, ppart, a, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k2 launch: %s", cudaGetErrorString(err));
+  prof_mark(3, stream);
   count_launch(3);
   return LEAFK_OK;
 }

@@ -35,14 +35,16 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
   // most of this kernel hides under K1's tail.  After any other producer: wait for the grid.
   if (a.done == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rows = g.B * g.F;
+  const int rows0 = g.B * g.F;
+  const int rows = a.q_out != nullptr ? 4 * rows0 : rows0;     // training: kinds 1..3 are rows of their own (after the PCEN rows)
   const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;       // clip length <= 2^30 (checked on the host)
   const int n_end = g.n_begin + g.n_count;
   const int FV = a.q_out != nullptr ? 4 * g.F : g.F;            // virtual filters per (clip, tile) block
   const size_t tile_stride = (size_t)FV * g.SL;
 
   for (int row = blockIdx.x * K2_WARPS + warp; row < rows; row += gridDim.x * K2_WARPS) {
-    const int b = row / g.F, f = row - b * g.F;
+    const int kind = row / rows0, r0 = row - kind * rows0;
+    const int b = r0 / g.F, f = r0 - b * g.F;
     if (a.done != nullptr) {
       if (lane == 0) {
         const int* flag = a.done + b;
@@ -64,7 +66,26 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
       }
       __syncwarp();
     }
-    const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + (size_t)f * g.SL;
+    const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + ((size_t)kind * g.F + f) * g.SL;
+    if (kind > 0) {
+      // pooled bilinear form of the parameter gradients (training forward): assembled like p, tile order, no bias
+      float* qrow = a.q_out + (size_t)(kind - 1) * rows0 * g.n_count + (size_t)r0 * g.n_count;
+      for (int n = g.n_begin + lane; n < n_end; n += 32) {
+        int wlo = n * g.H - g.padL, whi = wlo + g.K - 1;
+        if (wlo < te_lo) wlo = te_lo;
+        if (whi > te_hi - 1) whi = te_hi - 1;
+        const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
+        float s = 0.f;
+        for (int i = i0; i <= i1; ++i) {
+          const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
+          int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
+          if (nf < g.n_begin) nf = g.n_begin;
+          s += __ldcg(pbase + (size_t)i * tile_stride + (n - nf));
+        }
+        qrow[n - g.n_begin] = s;
+      }
+      continue;
+    }
     const size_t ooff = (size_t)b * a.ldo_b + (size_t)f * a.ldo_f;
     float* orow = a.out + ooff;
     __nv_bfloat16* orow16 = reinterpret_cast<__nv_bfloat16*>(a.out) + ooff;
@@ -155,32 +176,6 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
           if (prow) prow[n - g.n_begin] = p[u];
         }
       }
-      if (a.q_out != nullptr) {
-        // training forward: the pooled bilinear forms of the parameter gradients, assembled like p (tile order)
-        const size_t qstride = (size_t)g.B * g.F * g.n_count;
-        float* qrow = a.q_out + ((size_t)b * g.F + f) * g.n_count;
-#pragma unroll 1
-        for (int kind = 1; kind < 4; ++kind) {
-          const float* qbase = pbase + (size_t)kind * g.F * g.SL;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int n = n0 + 32 * u + lane;
-            if (!ok[u]) continue;
-            int wlo = n * g.H - g.padL, whi = wlo + g.K - 1;
-            if (wlo < te_lo) wlo = te_lo;
-            if (whi > te_hi - 1) whi = te_hi - 1;
-            const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
-            float s = 0.f;
-            for (int i = i0; i <= i1; ++i) {
-              const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
-              int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
-              if (nf < g.n_begin) nf = g.n_begin;
-              s += __ldcg(qbase + (size_t)i * tile_stride + (n - nf));
-            }
-            qrow[(size_t)(kind - 1) * qstride + (n - g.n_begin)] = s;
-          }
-        }
-      }
     }
     if (a.compression && a.ema_out != nullptr && lane == 0) a.ema_out[(size_t)b * g.F + f] = carry;
   }
@@ -190,7 +185,7 @@ cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cuda
   int tl_shift = 0;
   while ((1 << tl_shift) < g.TL) ++tl_shift;
   if ((1 << tl_shift) != g.TL) return cudaErrorInvalidValue;   // tile lengths are powers of two
-  const long long rows = (long long)g.B * g.F;
+  const long long rows = (long long)g.B * g.F * (a.q_out != nullptr ? 4 : 1);
   // one warp per row; blocks beyond the resident wave are scheduled as earlier ones retire (rows past 2^31/8
   // blocks loop inside the kernel)
   long long blocks = (rows + K2_WARPS - 1) / K2_WARPS;

@@ -49,7 +49,7 @@ struct ProfRec { cudaEvent_t ev[4]; };
 thread_local bool g_prof_on = false;
 thread_local ProfRec g_prof[1024];
 thread_local int g_prof_n = 0;
-static void prof_mark(int which, cudaStream_t stream) {
+void prof_mark(int which, cudaStream_t stream) {
   if (!g_prof_on || g_prof_n >= 1024) return;
   if (which == 0)
     for (int i = 0; i < 4; ++i) cudaEventCreate(&g_prof[g_prof_n].ev[i]);
