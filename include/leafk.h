@@ -85,6 +85,21 @@ typedef struct leafk_grads {
   float* ema_w;
 } leafk_grads;
 
+/* Optional per-clip preparation applied while the kernels stage the waveform (nothing is written back): what the
+ * reference's data pipeline does on the CPU before Leaf.forward -- PadToSize('wrap') / CenterCrop / RandomCrop
+ * (utilities/data/raw_transforms.py:121-160), the collate function's zero padding (utilities/data/utils.py:8-28) and
+ * PeakNormalization(only_too_loud_sounds) (raw_transforms.py:334-344).  Sample i (0 <= i < T) of prepared clip b is
+ * raw[b*ld + (i + start[b])] when 0 <= i + start[b] < length[b]; outside that range the index wraps around modulo
+ * length[b] (wrap != 0) or the sample is zero; the value is divided by divisor[b].  Any pointer may be NULL
+ * (start 0, length T, divisor 1).  All arrays are DEVICE pointers of B entries. */
+typedef struct leafk_clip_prep {
+  const int* start;
+  const int* length;
+  const float* divisor;
+  long long ld;   /* row stride of the raw waveform buffer in samples; 0 = T */
+  int wrap;
+} leafk_clip_prep;
+
 /* Static configuration: what Leaf.__init__ derives (frontend.py:38-39, 65-73, 84). */
 typedef struct leafk_config {
   int F;           /* n_filters                                                     */
@@ -98,6 +113,9 @@ typedef struct leafk_config {
                       in the kernel as s/32768 (what soundfile hands the reference's data pipeline,
                       utilities/data/utils.py:136-157); halves the HBM / PCIe bytes of the waveform */
   int output_format;/* LEAFK_OUTPUT_F32 (reference) or LEAFK_OUTPUT_BF16 */
+  const leafk_clip_prep* prep; /* NULL (reference: the batch is used as it is) or the per-clip preparation above; honoured
+                      by leafk_forward, leafk_forward_window, leafk_forward_train and leafk_backward (host-buffer calls
+                      and the waveform gradient reject it) */
 } leafk_config;
 
 int leafk_version(void);
@@ -112,6 +130,12 @@ void leafk_same_padding(int K, int* pad_left, int* pad_right);
 /* Bytes of device scratch leafk_forward / leafk_forward_window / leafk_backward need for B clips
  * when producing `n_frames` frames per clip. */
 size_t leafk_workspace_bytes(const leafk_config* cfg, int B, int n_frames);
+
+/* Peak-normalisation divisors of the B prepared clips described by cfg->prep (its `divisor` member is ignored here):
+ * divisor_out[b] = max_i |sample i| when that exceeds 1 (only_too_loud != 0; the reference's setting) or is non-zero
+ * (only_too_loud == 0), else 1.  One pass over the waveform; use the result as leafk_clip_prep.divisor. */
+int leafk_peak_divisors(const leafk_config* cfg, const float* x, int B, int T, int only_too_loud,
+                        float* divisor_out, void* stream);
 
 /* Whole-clip forward: replaces Leaf.forward (frontend.py:78-89).
  *   x    (B,1,T) contiguous fp32                      -> out (B,F,N) contiguous fp32
@@ -171,6 +195,20 @@ int leafk_backward_saved(const leafk_config* cfg, const leafk_params* prm, const
  * call (a synchronous 4-byte read -- call it after synchronising the stream) returns LEAFK_ETIMEOUT then. */
 int leafk_async_status(const void* workspace);
 
+/* ---- the two stages the reference's constructor declares but does not implement (frontend.py:40-41, 62-63) -------
+ * Stand-alone kernels around the fused frontend, forward and backward each; semantics of the original LEAF.
+ * Pre-emphasis: y[b,t] = w2[0] x[b,t] + w2[1] x[b,t+1] with x[b,T] = 0 (learnable 2-tap 'same' correlation, initial
+ * value (-0.97, 1)).  Backward: grad_x (B,T) or NULL, grad_w2 (2).
+ * Mean/variance normalisation: every row of N frames is centred and scaled by its own biased standard deviation,
+ * out = (v - mean) / sqrt(var + eps); stats (rows,2) receives (mean, 1/sqrt(var+eps)) for the backward. */
+int leafk_preemp_forward(const float* x, const float* w2, int B, int T, float* y, void* stream);
+size_t leafk_preemp_backward_workspace_bytes(void);
+int leafk_preemp_backward(const float* x, const float* w2, const float* grad_y, int B, int T, float* grad_x,
+                          float* grad_w2, void* workspace, size_t workspace_bytes, void* stream);
+int leafk_instnorm_forward(const float* v, long long rows, int N, float eps, float* out, float* stats, void* stream);
+int leafk_instnorm_backward(const float* v, const float* stats, const float* grad_out, long long rows, int N,
+                            float* grad_v, void* stream);
+
 /* End-to-end call on HOST buffers: x_host (B,1,T) and out_host (B,F,N) are host pointers
  * (pinned for full speed).  The H2D copy is enqueued on copy_stream in `n_slices` (<= 32) pieces,
  * each followed by a stream-ordered 32-bit flag write; ONE persistent launch of the tensor-core
@@ -221,7 +259,7 @@ int leafk_profile_k1_clock(const leafk_config* cfg, int B, int T, const void* wo
 int leafk_profile_tc_schedule(const leafk_config* cfg, int B, int T, const void* workspace, size_t workspace_bytes,
                               int* n_groups, int* channels_per_group, int* n_ksteps, int* codes, int codes_capacity);
 
-/* Introspection used by tests / bench: kernels launched by this thread since the last reset. */
+/* Introspection used by tests / bench: kernels launched by this process since the last reset. */
 long long leafk_launch_count(int reset);
 
 #ifdef __cplusplus

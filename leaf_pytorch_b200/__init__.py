@@ -5,8 +5,9 @@ from .frontend import Leaf
 from .frontend_helper import get_frontend
 from .functional import LeafSpec, leaf_forward, forward_raw, forward_window, launch_count
 from ._native import LeafNativeError, LIB_PATH
-from . import integration, streaming, distributed, serving
+from . import integration, streaming, distributed, serving, classifier
 from .serving import HostPipeline
+from .classifier import Classifier
 
 __all__ = ["Leaf", "get_frontend", "LeafSpec", "leaf_forward", "forward_raw", "forward_window",
-           "launch_count", "LeafNativeError", "LIB_PATH", "HostPipeline"]
+           "launch_count", "LeafNativeError", "LIB_PATH", "HostPipeline", "Classifier"]

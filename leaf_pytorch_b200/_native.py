@@ -25,7 +25,9 @@ SYMBOLS = (
     "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end", "leafk_profile_k1_clock", "leafk_profile_tc_schedule",
     "leafk_forward_host_async", "leafk_event_create", "leafk_event_destroy", "leafk_event_synchronize",
     "leafk_train_supported", "leafk_train_workspace_bytes", "leafk_forward_train", "leafk_backward_saved",
-    "leafk_backward_saved_workspace_bytes", "leafk_async_status",
+    "leafk_backward_saved_workspace_bytes", "leafk_async_status", "leafk_peak_divisors",
+    "leafk_preemp_forward", "leafk_preemp_backward", "leafk_preemp_backward_workspace_bytes", "leafk_instnorm_forward",
+    "leafk_instnorm_backward",
 )
 
 
@@ -41,10 +43,16 @@ class Grads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("kernel", "pool_w", "pool_b", "alpha", "delta", "root", "ema_w")]
 
 
+class ClipPrep(C.Structure):
+    """leafk_clip_prep: per-clip crop start / raw length / peak divisor applied while the kernels stage the waveform."""
+    _fields_ = [("start", C.c_void_p), ("length", C.c_void_p), ("divisor", C.c_void_p), ("ld", C.c_longlong),
+                ("wrap", C.c_int)]
+
+
 class Config(C.Structure):
     _fields_ = [("F", C.c_int), ("K", C.c_int), ("H", C.c_int), ("pcen_floor", C.c_float),
                 ("clamp_min", C.c_float), ("compression", C.c_int), ("algo", C.c_int), ("input_format", C.c_int),
-                ("output_format", C.c_int)]
+                ("output_format", C.c_int), ("prep", C.POINTER(ClipPrep))]
 
 
 _lib = None
@@ -117,6 +125,18 @@ def lib() -> C.CDLL:
         L.leafk_backward_saved.restype = i
         L.leafk_backward_saved.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, vp, C.POINTER(Grads),
                                            vp, vp, sz, vp]
+        L.leafk_peak_divisors.restype = i
+        L.leafk_peak_divisors.argtypes = [C.POINTER(Config), vp, i, i, i, vp, vp]
+        L.leafk_preemp_forward.restype = i
+        L.leafk_preemp_forward.argtypes = [vp, vp, i, i, vp, vp]
+        L.leafk_preemp_backward_workspace_bytes.restype = sz
+        L.leafk_preemp_backward_workspace_bytes.argtypes = []
+        L.leafk_preemp_backward.restype = i
+        L.leafk_preemp_backward.argtypes = [vp, vp, vp, i, i, vp, vp, vp, sz, vp]
+        L.leafk_instnorm_forward.restype = i
+        L.leafk_instnorm_forward.argtypes = [vp, ll, i, C.c_float, vp, vp, vp]
+        L.leafk_instnorm_backward.restype = i
+        L.leafk_instnorm_backward.argtypes = [vp, vp, vp, ll, i, vp, vp]
         L.leafk_async_status.restype = i
         L.leafk_async_status.argtypes = [vp]
         L.leafk_launch_count.restype = ll

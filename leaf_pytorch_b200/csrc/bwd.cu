@@ -38,6 +38,7 @@ void launch_k0(const float* kernel, const float* pool_w, int F, int K, int Kp, i
                float prune_c, float prune_c3, int* done, int n_done, cudaStream_t stream);
 void launch_k0_train(const float* kernel, const float* pool_w, int F, int K, int Kp, int FB, int n_groups,
                      float* tprm, uint8_t* w16t, int* done, int n_done, cudaStream_t stream);
+void geom_apply_prep(const leafk_config* cfg, Geom* g);
 void bank_bounds(int K, float* mu_hi, float* sigma_lo, float* sigma_hi, float* pool_lo);
 int k1_tc_train_filters_per_group(int K, int H);
 cudaError_t launch_k1_tc_train(const Geom& g, const float* x, const uint8_t* w16t, int FB, int n_groups,
@@ -256,10 +257,10 @@ bwd_generic_kernel(const Geom g, const GenericArgs a) {
     const long long t = ts + tid;
     const bool tok = t < g.T_total;
     __syncthreads();                                  // previous unit done with xs / dxs
-    const size_t xrow = (size_t)b * g.ldx;
+    const ClipView cv = clip_view(g, b);
     for (int i = tid; i < WL; i += G_TL) {
       const long long s = ts - g.padL + i;
-      xs[i] = (s >= 0 && s < g.T_total) ? load_sample(a.x, xrow, s, g.x_fmt) : 0.f;
+      xs[i] = (s >= 0 && s < g.T_total) ? clip_sample(g, a.x, cv, s) : 0.f;
       if (DX) dxs[i] = 0.f;
     }
     // frames whose pooling window holds sample t: k = t + padL - n H in [0, K)
@@ -466,6 +467,7 @@ static void whole_clip_geom(const leafk_config* cfg, int B, int T, int tile_len,
   g.te_lo = 0; g.te_hi = T; g.TL = tile_len; g.n_tiles = (T + tile_len - 1) / tile_len;
   g.SL = (tile_len + K - 2) / H + 1;
   g.x_fmt = cfg->input_format == LEAFK_INPUT_S16 ? 1 : 0;
+  geom_apply_prep(cfg, &g);
   *out = g;
 }
 
@@ -588,6 +590,8 @@ static int backward_core(const leafk_config* cfg, const leafk_params* prm, const
   if ((need_generic || want_dx) && !x) return fail(LEAFK_EINVAL, "the waveform is needed for this backward");
   if (want_dx && cfg->input_format == LEAFK_INPUT_S16)
     return fail(LEAFK_EINVAL, "no gradient w.r.t. an int16 waveform");
+  if (want_dx && cfg->prep)
+    return fail(LEAFK_EINVAL, "no gradient w.r.t. a waveform that is cropped / normalised on the fly (cfg->prep)");
   BwdPlan pl;
   bwd_plan(cfg, B, T, need_generic, want_dx, &pl);
   if (pl.total > workspace_bytes)

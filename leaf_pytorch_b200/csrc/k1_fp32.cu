@@ -51,12 +51,12 @@ k1_fp32_kernel(const Geom g, const float* __restrict__ x, const float* __restric
   const int n_first = first_frame_of(g, ts);
 
   // ---- stage the sample window: xs[i] = x~[ts - padL + i], zero outside the clip -------------
-  const size_t xrow = (size_t)b * g.ldx;
+  const ClipView cv = clip_view(g, b);
   for (int i = tid; i < XS; i += blockDim.x) {
     const long long a = ts - g.padL + i;
     const long long wi = a - g.t_off;
     float v = 0.f;
-    if (a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win) v = load_sample(x, xrow, wi, g.x_fmt);
+    if (a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win) v = clip_sample(g, x, cv, wi);
     xs[i] = v;
   }
   for (int i = tid; i < F32_NCH * g.SL * g.F; i += blockDim.x) pitem[i] = 0.f;

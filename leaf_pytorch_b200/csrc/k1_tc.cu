@@ -256,7 +256,7 @@ __device__ __forceinline__ void producer_loop(const Geom& g, const float* __rest
     const bool valid = u < n_units;                // odd unit count: the last pair's rank 1 runs on zeros
     const int b = valid ? (int)(u / g.n_tiles) : 0, tile = valid ? (int)(u % g.n_tiles) : 0;
     const long long ts = g.te_lo + (long long)tile * TILE;
-    const size_t xrow = (size_t)b * g.ldx;
+    const ClipView cv = clip_view(g, b);
     if (valid && rdy.ready != nullptr && ptid == 0 && !gave_up) {       // clip b still in flight over PCIe?
       const int* flag = rdy.ready + b / rdy.clips_per_flag;
       int v;
@@ -287,7 +287,7 @@ __device__ __forceinline__ void producer_loop(const Geom& g, const float* __rest
         const long long a = ts - g.padL + idx, wi = a - g.t_off;
         float val = 0.f;
         if (valid && jj < nchunk && idx < sp.LX && a >= 0 && a < g.T_total && wi >= 0 && wi < g.T_win)
-          val = load_sample(x, xrow, wi, g.x_fmt);   // coherent load: may have just landed
+          val = clip_sample(g, x, cv, wi);           // coherent load: may have just landed
         v[c][i] = val;
         mx = fmaxf(mx, fabsf(val));
       }

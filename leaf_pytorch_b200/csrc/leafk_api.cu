@@ -5,6 +5,7 @@
 #include "k1_tc_layout.cuh"
 #include "k2_pcen_args.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +27,8 @@ cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, cons
 constexpr int TC_TILE = 1024;
 // k2_pcen.cu
 cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cudaStream_t stream);
+// prep.cu
+void geom_apply_prep(const leafk_config* cfg, Geom* g);
 // bwd.cu
 int train_supported(int F, int K, int H);
 size_t train_workspace_bytes(const leafk_config* cfg, int B, int T);
@@ -41,7 +44,7 @@ int bwd_run(const leafk_config* cfg, const leafk_params* prm, const float* x, in
             void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 thread_local char g_err[512] = "";
-thread_local long long g_launches = 0;
+std::atomic<long long> g_launches{0};   // process-wide: the backward runs on autograd's own thread
 
 // Optional per-kernel timing (bench.py's roofline leg): between leafk_profile_begin() and
 // leafk_profile_end() every forward records 4 events on its stream (start, after K0, K1, K2).
@@ -95,6 +98,7 @@ static int make_geom(const leafk_config* cfg, int B, long long ldx, long long T_
   g.C2p = (g.C2 + 7) / 8 * 8;
   g.Kp = (cfg->K + 15) / 16 * 16;
   g.T_total = T_total; g.t_off = t_off; g.T_win = T_win; g.ldx = ldx;
+  geom_apply_prep(cfg, &g);
   g.N_total = (int)((T_total + g.padL + g.padR - g.K) / g.H + 1);
   if (n_begin < 0 || n_count < 1 || n_begin + n_count > g.N_total)
     return fail(LEAFK_EINVAL, "frame range [%d,%d) outside [0,%d)", n_begin, n_begin + n_count, g.N_total);
@@ -363,6 +367,7 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
                        size_t workspace_bytes, void* stream_, void* copy_stream_) {
   if (!cfg || !prm || !x_host || !out_host || !dev_x || !dev_out || !workspace)
     return fail(LEAFK_EINVAL, "null pointer argument");
+  if (cfg->prep) return fail(LEAFK_EINVAL, "host-buffer calls take prepared batches (cfg->prep must be NULL)");
   cudaStream_t stream = (cudaStream_t)stream_, cstream = (cudaStream_t)copy_stream_;
   const int N = leafk_num_frames(T, cfg->K, cfg->H);
   if (N < 1 || B < 1) return fail(LEAFK_EINVAL, "bad B/T");
@@ -424,6 +429,7 @@ int leafk_forward_host_async(const leafk_config* cfg, const leafk_params* prm, c
                              void* ev_compute_done_, void* ev_out_ready_) {
   if (!cfg || !prm || !x_host || !out_host || !dev_x || !dev_out || !workspace || !ev_compute_done_ || !ev_out_ready_)
     return fail(LEAFK_EINVAL, "null pointer argument");
+  if (cfg->prep) return fail(LEAFK_EINVAL, "host-buffer calls take prepared batches (cfg->prep must be NULL)");
   cudaStream_t stream = (cudaStream_t)stream_, cstream = (cudaStream_t)copy_stream_, dstream = (cudaStream_t)d2h_stream_;
   cudaEvent_t ev_compute_done = (cudaEvent_t)ev_compute_done_, ev_out_ready = (cudaEvent_t)ev_out_ready_;
   if (cstream == stream || dstream == stream || cstream == dstream)
@@ -587,9 +593,7 @@ int leafk_profile_tc_schedule(const leafk_config* cfg, int B, int T, const void*
 }
 
 long long leafk_launch_count(int reset) {
-  const long long v = g_launches;
-  if (reset) g_launches = 0;
-  return v;
+  return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
 }  // extern "C"

@@ -32,6 +32,23 @@ struct Geom {
   int n_tiles;             // tiles per clip
   int SL;                  // slots (frames) a tile can touch
   int x_fmt;               // 0: float32 samples, 1: int16 PCM (value = s / 32768)
+  // Optional on-the-fly clip preparation (reference data pipeline: PadToSize / CenterCrop / RandomCrop / the zero
+  // padding of the collate function / PeakNormalization, utilities/data/raw_transforms.py:121-140,143-160,334-344 and
+  // utilities/data/utils.py:8-28).  Sample i of prepared clip b is raw[(i + clip_start[b])] of its row, where indices
+  // outside [0, clip_len[b]) wrap around (clip_wrap) or read as zero, divided by clip_div[b].  All null: rows are
+  // used as they are.
+  const int* clip_start;
+  const int* clip_len;
+  const float* clip_div;
+  int clip_wrap;
+};
+
+// What a kernel needs to read clip b: row offset, crop start, raw length, divisor.
+struct ClipView {
+  size_t row;
+  long long start, len;
+  float div;
+  bool prep;
 };
 
 // sample i of a clip row (row = first sample of the clip in the window buffer)
@@ -39,6 +56,30 @@ __device__ __forceinline__ float load_sample(const float* base, size_t row_elems
   if (fmt == 0) return base[row_elems + i];
   return (float)reinterpret_cast<const short*>(base)[row_elems + i] * (1.0f / 32768.0f);
 }
+
+#ifdef __CUDACC__
+__device__ __forceinline__ ClipView clip_view(const Geom& g, int b) {
+  ClipView v;
+  v.row = (size_t)b * g.ldx;
+  v.prep = g.clip_start != nullptr || g.clip_len != nullptr || g.clip_div != nullptr;
+  v.start = g.clip_start ? g.clip_start[b] : 0;
+  v.len = g.clip_len ? g.clip_len[b] : g.T_total;
+  v.div = g.clip_div ? g.clip_div[b] : 1.0f;
+  return v;
+}
+// sample wi of the window (= sample t_off + wi of the prepared clip); the caller has checked 0 <= wi < T_win and that
+// the sample lies inside [0, T_total)
+__device__ __forceinline__ float clip_sample(const Geom& g, const float* x, const ClipView& v, long long wi) {
+  if (!v.prep) return load_sample(x, v.row, wi, g.x_fmt);
+  long long j = g.t_off + wi + v.start;
+  if (j < 0 || j >= v.len) {
+    if (!g.clip_wrap || v.len <= 0) return 0.f;
+    j %= v.len;
+    if (j < 0) j += v.len;
+  }
+  return load_sample(x, v.row, j, g.x_fmt) / v.div;
+}
+#endif
 
 __host__ __device__ inline long long floordiv_ll(long long a, long long b) {
   return (a >= 0) ? a / b : -((-a + b - 1) / b);

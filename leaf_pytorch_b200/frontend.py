@@ -54,9 +54,9 @@ class GaborConv1d(_FusedStage):
         self._strides = strides
         self._padding = padding
         self._use_bias = use_bias
+        # sort_filters (reference convolution.py:74-75 raises NotImplementedError): as in the original LEAF, the rows of
+        # the constrained kernel are ordered by centre frequency before the bank is synthesised
         self._sort_filters = sort_filters
-        if sort_filters:
-            raise NotImplementedError("sort filter functionality not yet implemented")
         if use_bias:
             raise NotImplementedError("the fused kernel has no per-channel conv bias (Leaf never enables it)")
         shape = (self._filters, 2)
@@ -77,6 +77,24 @@ class GaborConv1d(_FusedStage):
         # both complex formulations of the reference give the same filters (<=4e-9); the kernel
         # has a single synthesis path, the flag is kept for config compatibility only
         self.use_legacy_complex = use_legacy_complex
+
+
+class PreEmphasis(_FusedStage):
+    """Learnable 2-tap pre-emphasis (original LEAF; the reference declares ``preemp`` but raises, frontend.py:40-41).
+    ``weight`` has the shape of an nn.Conv1d(1, 1, 2, bias=False) kernel and starts at (-0.97, 1)."""
+
+    def __init__(self, coeff: float = 0.97):
+        super().__init__()
+        self.weight = nn.Parameter(torch.tensor([[[-coeff, 1.0]]], dtype=torch.float32))
+
+
+class InstanceNorm(_FusedStage):
+    """mean_var_norm (original LEAF; the reference raises, frontend.py:62-63): every (clip, filter) row is normalised
+    over its frames, no affine parameters (nn.InstanceNorm1d semantics, biased variance)."""
+
+    def __init__(self, eps: float = 1e-5):
+        super().__init__()
+        self.eps = eps
 
 
 class SquaredModulus(_FusedStage):
@@ -146,23 +164,20 @@ class Leaf(nn.Module):
                  window_stride: float = 10., preemp: bool = False, init_min_freq=60.0, init_max_freq=7800.0,
                  mean_var_norm: bool = False, pcen_compression: bool = True, use_legacy_complex=False,
                  initializer="default", algo: str = "auto", out_dtype: torch.dtype = torch.float32,
-                 out_layout: str = "bfn"):
+                 out_layout: str = "bfn", sort_filters: bool = False):
         super().__init__()
         window_size = int(sample_rate * window_len // 1000 + 1)
         hop = int(sample_rate * window_stride // 1000)
-        if preemp:
-            raise NotImplementedError("Pre-emp functionality not implemented yet..")
-        self._preemp = None
+        # preemp / mean_var_norm: the reference raises NotImplementedError for both; here they follow the original LEAF
+        self._preemp = PreEmphasis() if preemp else None
         if initializer == "default":
             initializer = MelGaborInit(sample_rate=sample_rate, min_freq=init_min_freq, max_freq=init_max_freq)
         self._complex_conv = GaborConv1d(filters=2 * n_filters, kernel_size=window_size, strides=1, padding="same",
-                                         use_bias=False, initializer=initializer,
+                                         use_bias=False, initializer=initializer, sort_filters=sort_filters,
                                          use_legacy_complex=use_legacy_complex)
         self._activation = SquaredModulus()
         self._pooling = GaussianLowPass(n_filters, kernel_size=window_size, strides=hop, padding="same")
-        self._instance_norm = None
-        if mean_var_norm:
-            raise NotImplementedError("Instance Norm functionality not added yet..")
+        self._instance_norm = InstanceNorm() if mean_var_norm else None
         if pcen_compression:
             self._compression = PCENLayer(n_filters, alpha=0.96, smooth_coef=0.04, delta=2.0, floor=1e-12,
                                           trainable=True, learn_smooth_coef=True, per_channel_smooth_coef=True)
@@ -189,7 +204,12 @@ class Leaf(nn.Module):
 
     def _param_tuple(self):
         pc = self._compression
-        return (self._complex_conv._kernel, self._pooling.weights, self._pooling._bias,
+        kernel = self._complex_conv._kernel
+        if self._complex_conv._sort_filters:
+            # order by the constrained centre frequency (original LEAF: argsort + gather on the clamped kernel)
+            order = torch.argsort(kernel.detach()[:, 0].clamp(0.0, math.pi), stable=True)
+            kernel = kernel[order]
+        return (kernel, self._pooling.weights, self._pooling._bias,
                 None if pc is None else pc.alpha, None if pc is None else pc.delta,
                 None if pc is None else pc.root, None if pc is None else pc.ema._weights)
 
@@ -200,7 +220,22 @@ class Leaf(nn.Module):
             # empty batch: the reference returns an empty (0,F,N) tensor (conv1d accepts B = 0)
             out = torch.zeros((0, self.spec.F, self.spec.num_frames(x.shape[2])), dtype=self.out_dtype, device=x.device)
         else:
+            if self._preemp is not None:
+                x = LF.pre_emphasis(x, self._preemp.weight)
             out = LF.leaf_forward(self.spec, x, *self._param_tuple())
+            if self._instance_norm is not None:
+                out = LF.instance_norm(out, self._instance_norm.eps)
+        return out.unsqueeze(1) if self.out_layout == "b1fn" else out
+
+    def forward_prepared(self, x_raw: torch.Tensor, n_samples: int, raw_lengths=None, starts="center",
+                         pad_mode: str = "wrap", peak_normalize: bool = True) -> torch.Tensor:
+        """Features of raw, unequal-length clips without a prepared copy of the batch: every clip is cropped
+        (``starts`` "center" or per-clip offsets) or padded (``pad_mode`` "wrap" / "zero") to ``n_samples`` and, when
+        its peak exceeds 1, peak-normalised -- the reference's per-clip transforms (utilities/data/raw_transforms.py:
+        121-160, 334-344; utilities/data/utils.py:8-28) -- inside the kernels' own staging of the waveform.
+        ``x_raw`` (B,1,Traw) float32 or int16 PCM on the GPU, ``raw_lengths`` (B,) true lengths."""
+        prep = LF.prepare_clips(self.spec, x_raw, n_samples, raw_lengths, starts, pad_mode, peak_normalize)
+        out = LF.leaf_forward(self.spec, x_raw, *self._param_tuple(), prep=prep)
         return out.unsqueeze(1) if self.out_layout == "b1fn" else out
 
     def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,

@@ -36,18 +36,72 @@ class LeafSpec:
     clamp_min: float = CLAMP_MIN
     out_dtype: torch.dtype = torch.float32    # torch.bfloat16: K2 writes bf16 features (inference; LEAFK_OUTPUT_BF16)
 
-    def config(self, input_dtype=torch.float32, reuse_banks: bool = False, out_dtype=None) -> N.Config:
+    def config(self, input_dtype=torch.float32, reuse_banks: bool = False, out_dtype=None, prep=None) -> N.Config:
         algo = N.ALGOS[self.algo] | (N.REUSE_BANKS if reuse_banks else 0)
         out_dtype = self.out_dtype if out_dtype is None else out_dtype
         if out_dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"out_dtype must be float32 or bfloat16, got {out_dtype}")
-        return N.Config(self.F, self.K, self.H, self.pcen_floor, self.clamp_min, int(self.compression),
-                        algo, 1 if input_dtype == torch.int16 else 0, 1 if out_dtype == torch.bfloat16 else 0)
+        cfg = N.Config(self.F, self.K, self.H, self.pcen_floor, self.clamp_min, int(self.compression),
+                       algo, 1 if input_dtype == torch.int16 else 0, 1 if out_dtype == torch.bfloat16 else 0, None)
+        if prep is not None:
+            cfg.prep = C.pointer(prep.struct)            # `prep` (and through it the device arrays) must outlive the call
+        return cfg
 
     def num_frames(self, T: int) -> int:
         lo = self.K // 2 + self.K % 2 - 1
         hi = self.K // 2
         return (T + lo + hi - self.K) // self.H + 1
+
+
+class ClipPrep:
+    """Per-clip preparation applied on the fly by the kernels (leafk_clip_prep): sample i of prepared clip b is
+    ``raw[b, 0, i + start[b]]`` inside ``[0, length[b])`` -- outside, the index wraps around (``wrap``) or the sample is
+    zero -- divided by ``divisor[b]``.  Built by :func:`prepare_clips`."""
+
+    def __init__(self, n_samples: int, start=None, length=None, divisor=None, ld: int = 0, wrap: bool = False):
+        self.n_samples = int(n_samples)
+        self.start, self.length, self.divisor = start, length, divisor
+        self.struct = N.ClipPrep(None if start is None else start.data_ptr(), None if length is None else length.data_ptr(),
+                                 None if divisor is None else divisor.data_ptr(), int(ld), int(bool(wrap)))
+
+
+def prepare_clips(spec: "LeafSpec", x_raw: torch.Tensor, n_samples: int, raw_lengths=None, starts="center",
+                  pad_mode: str = "wrap", peak_normalize: bool = True, only_too_loud: bool = True) -> ClipPrep:
+    """GPU side of the reference's per-clip input transforms: crop every raw clip to ``n_samples`` (``starts``:
+    "center" = CenterCrop, or an int tensor of crop offsets = RandomCrop drawn by the caller), pad shorter clips
+    (``pad_mode`` "wrap" = PadToSize('wrap'), "zero" = the collate function's zero padding) and, optionally, peak-
+    normalise clips whose peak exceeds 1 (PeakNormalization(only_too_loud_sounds)).  ``x_raw`` (B,1,Traw) float32 or
+    int16 on the GPU holds the raw clips row by row, ``raw_lengths`` (B,) their true lengths (default Traw).  Nothing is
+    copied: the result only describes the view; one small kernel computes the peak divisors."""
+    if not x_raw.is_cuda or x_raw.dim() != 3 or x_raw.shape[1] != 1 or not x_raw.is_contiguous():
+        raise ValueError("x_raw must be a contiguous CUDA tensor of shape (B,1,Traw)")
+    if pad_mode not in ("wrap", "zero"):
+        raise ValueError("pad_mode must be 'wrap' or 'zero'")
+    B, _, Traw = x_raw.shape
+    dev = x_raw.device
+    length = torch.full((B,), Traw, dtype=torch.int32, device=dev) if raw_lengths is None else \
+        torch.as_tensor(raw_lengths, dtype=torch.int32, device=dev).contiguous()
+    if length.numel() != B or int(length.max()) > Traw or int(length.min()) < 1:
+        raise ValueError("raw_lengths must hold B values in [1, Traw]")
+    if isinstance(starts, str):
+        if starts != "center":
+            raise ValueError("starts must be 'center' or a tensor of crop offsets")
+        # longer clips: (len - n)//2 (CenterCrop); shorter clips: -(n - len)//2, the offset PadToSize puts in front
+        diff = length.to(torch.int64) - n_samples
+        start = torch.where(diff >= 0, diff // 2, -((-diff) // 2)).to(torch.int32)
+    else:
+        start = torch.as_tensor(starts, dtype=torch.int32, device=dev).contiguous()
+        if start.numel() != B:
+            raise ValueError("starts must hold B crop offsets")
+    prep = ClipPrep(n_samples, start, length, None, ld=Traw, wrap=pad_mode == "wrap")
+    if peak_normalize:
+        div = torch.empty(B, dtype=torch.float32, device=dev)
+        cfg = spec.config(x_raw.dtype, prep=prep)
+        with torch.cuda.device(dev):
+            N.check(N.lib().leafk_peak_divisors(C.byref(cfg), _ptr(x_raw), B, int(n_samples), int(only_too_loud), _ptr(div),
+                                                _stream_ptr(dev)), "leafk_peak_divisors")
+        prep = ClipPrep(n_samples, start, length, div, ld=Traw, wrap=pad_mode == "wrap")
+    return prep
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -98,13 +152,16 @@ def _params_struct(spec: LeafSpec, kernel, pool_w, pool_b, alpha, delta, root, e
 
 
 def forward_raw(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w,
-                save_p: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """One fused forward on the current stream; no autograd.  Returns (out, saved_p or None)."""
+                save_p: bool = False, prep: Optional[ClipPrep] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """One fused forward on the current stream; no autograd.  Returns (out, saved_p or None).  With ``prep`` the
+    batch is ``prep.n_samples`` long per clip and ``x`` holds the raw rows (see prepare_clips)."""
     L = N.lib()
     x = _check_input(x)
     B, _, T = x.shape
+    if prep is not None:
+        T = prep.n_samples
     n = spec.num_frames(T)
-    cfg = spec.config(x.dtype)
+    cfg = spec.config(x.dtype, prep=prep)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
     with torch.cuda.device(x.device):
         out = torch.empty((B, spec.F, n), dtype=spec.out_dtype, device=x.device)
@@ -123,14 +180,16 @@ def train_supported(spec: LeafSpec) -> bool:
     return spec.algo != "fp32" and bool(N.lib().leafk_train_supported(spec.F, spec.K, spec.H))
 
 
-def forward_train_raw(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w):
+def forward_train_raw(spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w, prep: Optional[ClipPrep] = None):
     """Training forward on the current stream; no autograd.  Returns (out (B,F,N), saved (4,B,F,N)):
     saved[0] = floored pooled energies, saved[1:4] = pooled bilinear forms of the parameter gradients."""
     L = N.lib()
     x = _check_input(x)
     B, _, T = x.shape
+    if prep is not None:
+        T = prep.n_samples
     n = spec.num_frames(T)
-    cfg = spec.config(x.dtype, out_dtype=torch.float32)
+    cfg = spec.config(x.dtype, out_dtype=torch.float32, prep=prep)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x.device)
     with torch.cuda.device(x.device):
         out = torch.empty((B, spec.F, n), dtype=torch.float32, device=x.device)
@@ -205,23 +264,27 @@ class _LeafFunction(torch.autograd.Function):
     computed only when the waveform requires grad."""
 
     @staticmethod
-    def forward(ctx, spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w):
+    def forward(ctx, spec: LeafSpec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w, prep=None):
         if spec.out_dtype != torch.float32:
             raise TypeError("training needs float32 features (out_dtype=torch.bfloat16 is an inference option)")
+        if prep is not None and ctx.needs_input_grad[1]:
+            raise TypeError("no gradient with respect to a waveform that is cropped / normalised on the fly")
         ctx.spec = spec
+        ctx.prep = prep
         ctx.has_bias = pool_b is not None
         ctx.has_pcen = alpha is not None
         ctx.fused = train_supported(spec)
         if ctx.fused:
-            out, saved = forward_train_raw(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w)
+            out, saved = forward_train_raw(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w, prep=prep)
         else:
-            out, saved = forward_raw(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w, save_p=True)
+            out, saved = forward_raw(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w, save_p=True, prep=prep)
         # the waveform is needed again only by the generic backward and for its own gradient
         ctx.keep_x = (not ctx.fused) or ctx.needs_input_grad[1]
         tensors = [x if ctx.keep_x else None, saved, kernel, pool_w] + ([pool_b] if ctx.has_bias else []) + \
                   ([alpha, delta, root, ema_w] if ctx.has_pcen else [])
         ctx.save_for_backward(*tensors)
         ctx.x_shape, ctx.x_dtype = tuple(x.shape), x.dtype
+        ctx.n_samples = x.shape[2] if prep is None else prep.n_samples
         return out
 
     @staticmethod
@@ -239,10 +302,10 @@ class _LeafFunction(torch.autograd.Function):
         alpha = delta = root = ema_w = None
         if ctx.has_pcen:
             alpha, delta, root, ema_w = saved[idx:idx + 4]
-        B, _, T = ctx.x_shape
+        B, T = ctx.x_shape[0], ctx.n_samples
         if x is not None:
             x = _check_input(x)
-        cfg = spec.config(ctx.x_dtype, out_dtype=torch.float32)
+        cfg = spec.config(ctx.x_dtype, out_dtype=torch.float32, prep=ctx.prep)
         dev = p.device
         prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, dev)
         grad_out = grad_out.contiguous().to(torch.float32)
@@ -274,18 +337,97 @@ class _LeafFunction(torch.autograd.Function):
             return None if gt is None else gt.view(like.shape)
         return (None, gx, shaped(g[0], kernel), shaped(g[1], pool_w), shaped(g[2], pool_b) if pool_b is not None else None,
                 shaped(g[3], alpha) if alpha is not None else None, shaped(g[4], delta) if delta is not None else None,
-                shaped(g[5], root) if root is not None else None, shaped(g[6], ema_w) if ema_w is not None else None)
+                shaped(g[5], root) if root is not None else None, shaped(g[6], ema_w) if ema_w is not None else None, None)
 
 
-def leaf_forward(spec: LeafSpec, x, kernel, pool_w, pool_b=None, alpha=None, delta=None, root=None, ema_w=None):
-    """Differentiable fused LEAF forward: (B,1,T) float32 CUDA waveform -> (B,F,N)."""
+def leaf_forward(spec: LeafSpec, x, kernel, pool_w, pool_b=None, alpha=None, delta=None, root=None, ema_w=None,
+                 prep: Optional[ClipPrep] = None):
+    """Differentiable fused LEAF forward: (B,1,T) float32 CUDA waveform -> (B,F,N).  ``prep``: per-clip crop / pad /
+    peak normalisation applied on the fly (prepare_clips); ``x`` then holds the raw clips."""
     if spec.compression and any(t is None for t in (alpha, delta, root, ema_w)):
         raise ValueError("compression=True needs alpha, delta, root and ema_w")
     tensors = (x, kernel, pool_w, pool_b, alpha, delta, root, ema_w)
     if not torch.is_grad_enabled() or not any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
         # inference: nothing is saved for a backward that will not come
-        return forward_raw(spec, x, *[None if t is None else t.detach() for t in tensors[1:]])[0]
-    return _LeafFunction.apply(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w)
+        return forward_raw(spec, x, *[None if t is None else t.detach() for t in tensors[1:]], prep=prep)[0]
+    return _LeafFunction.apply(spec, x, kernel, pool_w, pool_b, alpha, delta, root, ema_w, prep)
+
+
+class _PreEmphasis(torch.autograd.Function):
+    """y[b,0,t] = w[0] x[b,0,t] + w[1] x[b,0,t+1]  (x[T] = 0): leafk_preemp_forward / leafk_preemp_backward."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        L = N.lib()
+        x = _check_input(x)
+        if x.dtype != torch.float32:
+            raise TypeError("pre-emphasis needs a float32 waveform")
+        w2 = _check_param("preemp weight", w, 2, x.device)
+        B, _, T = x.shape
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            N.check(L.leafk_preemp_forward(_ptr(x), _ptr(w2), B, T, _ptr(y), _stream_ptr(x.device)), "leafk_preemp_forward")
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        L = N.lib()
+        x, w = ctx.saved_tensors
+        w2 = _check_param("preemp weight", w, 2, x.device)
+        B, _, T = x.shape
+        gy = gy.contiguous().to(torch.float32)
+        with torch.cuda.device(x.device):
+            gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+            gw = torch.empty(2, dtype=torch.float32, device=x.device)
+            nws = int(L.leafk_preemp_backward_workspace_bytes())
+            ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+            N.check(L.leafk_preemp_backward(_ptr(x), _ptr(w2), _ptr(gy), B, T, _ptr(gx), _ptr(gw), _ptr(ws), nws,
+                                            _stream_ptr(x.device)), "leafk_preemp_backward")
+        return gx, gw.view(w.shape)
+
+
+def pre_emphasis(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """Learnable 2-tap pre-emphasis in front of the Gabor bank (original LEAF; reference frontend.py:40-41 stub)."""
+    return _PreEmphasis.apply(x, weight)
+
+
+class _InstanceNorm(torch.autograd.Function):
+    """Per-(clip, filter) mean / variance normalisation over frames: leafk_instnorm_forward / _backward."""
+
+    @staticmethod
+    def forward(ctx, v, eps):
+        L = N.lib()
+        if not v.is_cuda or v.dtype != torch.float32 or v.dim() != 3:
+            raise TypeError("instance norm expects float32 CUDA features of shape (B,F,N)")
+        v = v.contiguous()
+        rows, n = v.shape[0] * v.shape[1], v.shape[2]
+        out = torch.empty_like(v)
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=v.device)
+        with torch.cuda.device(v.device):
+            N.check(L.leafk_instnorm_forward(_ptr(v), rows, n, float(eps), _ptr(out), _ptr(stats), _stream_ptr(v.device)),
+                    "leafk_instnorm_forward")
+        ctx.save_for_backward(v, stats)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        L = N.lib()
+        v, stats = ctx.saved_tensors
+        rows, n = v.shape[0] * v.shape[1], v.shape[2]
+        g = g.contiguous().to(torch.float32)
+        gv = torch.empty_like(v)
+        with torch.cuda.device(v.device):
+            N.check(L.leafk_instnorm_backward(_ptr(v), _ptr(stats), _ptr(g), rows, n, _ptr(gv), _stream_ptr(v.device)),
+                    "leafk_instnorm_backward")
+        return gv, None
+
+
+def instance_norm(v: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """mean_var_norm of the original LEAF (reference frontend.py:62-63 stub): nn.InstanceNorm1d without affine."""
+    return _InstanceNorm.apply(v, eps)
 
 
 _host_cache = {}                 # (device, shapes, geometry, algo, dtype) -> device scratch of forward_host

@@ -63,10 +63,13 @@ def test_initial_gabor_parameters_bit_identical_to_reference(name):
 
 
 def test_error_behaviour_matches_reference():
-    with pytest.raises(NotImplementedError):
-        L.Leaf(preemp=True)
-    with pytest.raises(NotImplementedError):
-        L.Leaf(mean_var_norm=True)
+    # preemp / mean_var_norm / sort_filters: the reference only declares them (NotImplementedError, frontend.py:40-41,
+    # 62-63, convolution.py:74-75); here they are implemented with the original LEAF's semantics and
+    # add no state unless switched on
+    assert set(L.Leaf(mean_var_norm=True, sort_filters=True).state_dict()) == set(L.Leaf().state_dict())
+    assert set(L.Leaf(preemp=True).state_dict()) - set(L.Leaf().state_dict()) == {"_preemp.weight"}
+    assert L.Leaf(preemp=True)._preemp.weight.detach().reshape(-1).tolist() == pytest.approx([-0.97, 1.0])
+    assert L.Leaf()._preemp is None and L.Leaf()._instance_norm is None
     with pytest.raises(ValueError):
         L.Leaf(initializer="nonsense")
     with pytest.raises(NotImplementedError):
@@ -248,7 +251,7 @@ def test_header_constants_match_the_python_binding():
     flags = [defs["LEAFK_TC_NOPRUNE"], defs["LEAFK_REUSE_BANKS"]]
     assert all(f > 15 and f & (f - 1) == 0 for f in flags) and len(set(flags)) == 2     # distinct bits above the kernel choice
     body = re.search(r"typedef struct leafk_config \{(.*?)\} leafk_config;", text, re.S).group(1)
-    fields = re.findall(r"^\s*(?:int|float)\s+(\w+);", body, re.M)
+    fields = re.findall(r"^\s*(?:int|float|const leafk_clip_prep\*)\s+(\w+);", body, re.M)
     assert fields == [n for n, _ in N.Config._fields_]
 
 
