@@ -26,8 +26,15 @@ constexpr int K2_WARPS = 8;
 // a negative delta gives NaN exactly like powf / the reference).
 __device__ __forceinline__ float pow_pos(float x, float y) { return exp2f(y * log2f(x)); }
 
+// ROWBLOCK = false: one warp per (clip, filter) row (many short rows: 1 s clips).  ROWBLOCK = true: one block of 8 warps
+// per row, for long rows (10 s / 60 s clips, N >= 512 frames): the smoother is a chain along the frames, so a single
+// warp walks a 1000-frame row in 8 dependent steps of 128 frames while most of the GPU idles (512 rows at F=64, B=8).
+// Here warp w takes the frames [n0 + 128 w, n0 + 128 w + 128) of a 1024-frame super-step, publishes the composite
+// affine map of its segment, and picks up its carry-in by composing the maps of the warps before it (<= 7 FMAs).
+template <bool ROWBLOCK>
 __global__ void __launch_bounds__(K2_WARPS * 32)
 k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, int tl_shift, unsigned long long hop_magic) {
+  __shared__ float s_A[K2_WARPS], s_C[K2_WARPS], s_first;
   // Programmatic dependent launch: this grid is scheduled under the tail of the kernel that writes the partial sums.
   // After the tensor-core K1 it does not wait for that whole grid: K1 counts, per clip, the tiles whose partial sums are
   // stored (release), and a row starts as soon as its clip is complete (acquire) -- clips finish in index order and
@@ -42,7 +49,8 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
   const int FV = a.q_out != nullptr ? 4 * g.F : g.F;            // virtual filters per (clip, tile) block
   const size_t tile_stride = (size_t)FV * g.SL;
 
-  for (int row = blockIdx.x * K2_WARPS + warp; row < rows; row += gridDim.x * K2_WARPS) {
+  for (int row = ROWBLOCK ? blockIdx.x : blockIdx.x * K2_WARPS + warp; row < rows;
+       row += ROWBLOCK ? gridDim.x : gridDim.x * K2_WARPS) {
     const int kind = row / rows0, r0 = row - kind * rows0;
     const int b = r0 / g.F, f = r0 - b * g.F;
     if (a.done != nullptr) {
@@ -98,7 +106,8 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
 
     // 128 frames per step: 4 independent groups of 32 consecutive frames (lane = frame within group), so the
     // loads, the 4 local scans and the 4 PCEN evaluations of a step overlap; only 4 FMAs chain the carry.
-    for (int n0 = g.n_begin; n0 < n_end; n0 += 128) {
+    for (int nb0 = g.n_begin; nb0 < n_end; nb0 += ROWBLOCK ? 128 * K2_WARPS : 128) {
+      const int n0 = nb0 + (ROWBLOCK ? 128 * warp : 0);
       float p[4];
       bool ok[4];
       // partial pooled sums first (the longest latency of the row), parameters while they are in flight
@@ -144,7 +153,13 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
       float o[4] = {p[0], p[1], p[2], p[3]};
       if (a.compression) {
         if (!have_carry) {                                    // smoother starts at the first frame
-          carry = __shfl_sync(0xffffffffu, p[0], 0);          // postprocessing.py:15
+          if constexpr (ROWBLOCK) {
+            if (warp == 0 && lane == 0) s_first = p[0];
+            __syncthreads();
+            carry = s_first;
+          } else {
+            carry = __shfl_sync(0xffffffffu, p[0], 0);        // postprocessing.py:15
+          }
           have_carry = true;
         }
         float A[4], C[4];
@@ -158,6 +173,27 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
             if (lane >= d) { C[u] = fmaf(A[u], Cp, C[u]); A[u] *= Ap; }
           }
         }
+        float next_carry = 0.f;
+        if constexpr (ROWBLOCK) {
+          // composite map of this warp's 128 frames, then the carry-in from the warps before it
+          float Aw = 1.f, Cw = 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float At = __shfl_sync(0xffffffffu, A[u], 31), Ct = __shfl_sync(0xffffffffu, C[u], 31);
+            Cw = fmaf(At, Cw, Ct); Aw *= At;
+          }
+          __syncthreads();                                    // previous super-step's maps consumed
+          if (lane == 0) { s_A[warp] = Aw; s_C[warp] = Cw; }
+          __syncthreads();
+          float c_in = carry, c_all = carry;
+#pragma unroll
+          for (int k = 0; k < K2_WARPS; ++k) {
+            c_all = fmaf(s_A[k], c_all, s_C[k]);
+            if (k + 1 == warp) c_in = c_all;
+          }
+          next_carry = c_all;
+          carry = c_in;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float m = fmaf(A[u], carry, C[u]);            // smoother state after this lane's frame
@@ -166,6 +202,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
           const float uu = p[u] / pow_pos(dd, alpha) + delta; // postprocessing.py:66
           o[u] = pow_pos(uu, q) - dq;
         }
+        if constexpr (ROWBLOCK) carry = next_carry;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -177,7 +214,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
         }
       }
     }
-    if (a.compression && a.ema_out != nullptr && lane == 0) a.ema_out[(size_t)b * g.F + f] = carry;
+    if (a.compression && a.ema_out != nullptr && lane == 0 && (!ROWBLOCK || warp == 0)) a.ema_out[(size_t)b * g.F + f] = carry;
   }
 }
 
@@ -186,9 +223,11 @@ cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cuda
   while ((1 << tl_shift) < g.TL) ++tl_shift;
   if ((1 << tl_shift) != g.TL) return cudaErrorInvalidValue;   // tile lengths are powers of two
   const long long rows = (long long)g.B * g.F * (a.q_out != nullptr ? 4 : 1);
-  // one warp per row; blocks beyond the resident wave are scheduled as earlier ones retire (rows past 2^31/8
-  // blocks loop inside the kernel)
-  long long blocks = (rows + K2_WARPS - 1) / K2_WARPS;
+  // long rows: one block per row (the choice depends on the frame count only, so a clip's features do not depend on
+  // the batch it is in); else one warp per row.  Blocks beyond the resident wave are scheduled as earlier ones
+  // retire (rows past the grid limit loop inside the kernel)
+  const bool rowblock = a.q_out == nullptr && g.n_count >= 512;
+  long long blocks = rowblock ? rows : (rows + K2_WARPS - 1) / K2_WARPS;
   if (blocks > (1LL << 20)) blocks = 1LL << 20;
   const unsigned long long hop_magic = div_magic_of((unsigned)g.H);
   cudaLaunchConfig_t lc = {};
@@ -197,7 +236,8 @@ cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cuda
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at; lc.numAttrs = 1;
-  return cudaLaunchKernelEx(&lc, k2_pcen_kernel, g, ppart, a, tl_shift, hop_magic);
+  if (rowblock) return cudaLaunchKernelEx(&lc, k2_pcen_kernel<true>, g, ppart, a, tl_shift, hop_magic);
+  return cudaLaunchKernelEx(&lc, k2_pcen_kernel<false>, g, ppart, a, tl_shift, hop_magic);
 }
 
 }  // namespace leafk
