@@ -115,14 +115,17 @@ bwd_pcen_kernel(int B, int F, int N, const PcenBwdArgs a) {
         const float prev = state;
         state = fmaf(om, state, w * p[j]);
         if (nl < seg_n) {
+          // one log2 + one exp2 per power (D, u > 0 wherever the forward is finite); ln = log2 * ln 2
           const float D = a.pcen_floor + state;
-          const float Dma = 1.0f / powf(D, alpha);
+          const float l2D = log2f(D);
+          const float Dma = exp2f(-alpha * l2D);
           const float u = p[j] * Dma + delta;
-          const float uq1 = powf(u, q - 1.0f);
+          const float l2u = log2f(u);
+          const float uq1 = exp2f((q - 1.0f) * l2u);
           const float G = go[j] * q * uq1;
           s_delta += G - go[j] * q * dq1;
-          s_alpha -= G * p[j] * Dma * logf(D);
-          s_root -= go[j] * (u * uq1 * logf(u) - dq * ldelta) * (q * q);
+          s_alpha -= G * p[j] * Dma * (l2D * 0.69314718056f);
+          s_root -= go[j] * (u * uq1 * (l2u * 0.69314718056f) - dq * ldelta) * (q * q);
           float* sc = a.scratch + (row + seg0 + nl) * 3;
           sc[0] = G * Dma;
           sc[1] = -G * alpha * p[j] * Dma / D;
@@ -532,7 +535,7 @@ int forward_train_run(const leafk_config* cfg, const leafk_params* prm, const fl
   err = launch_k2(g, ppart, a, stream);
   if (err != cudaSuccess) return fail(LEAFK_ECUDA, "k2 launch: %s", cudaGetErrorString(err));
   prof_mark(3, stream);
-  count_launch(3);
+  count_launch(4);
   return LEAFK_OK;
 }
 

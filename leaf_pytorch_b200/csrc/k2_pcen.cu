@@ -42,8 +42,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
   // most of this kernel hides under K1's tail.  After any other producer: wait for the grid.
   if (a.done == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int rows0 = g.B * g.F;
-  const int rows = a.q_out != nullptr ? 4 * rows0 : rows0;     // training: kinds 1..3 are rows of their own (after the PCEN rows)
+  const int rows = g.B * g.F;
   const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;       // clip length <= 2^30 (checked on the host)
   const int n_end = g.n_begin + g.n_count;
   const int FV = a.q_out != nullptr ? 4 * g.F : g.F;            // virtual filters per (clip, tile) block
@@ -51,8 +50,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
 
   for (int row = ROWBLOCK ? blockIdx.x : blockIdx.x * K2_WARPS + warp; row < rows;
        row += ROWBLOCK ? gridDim.x : gridDim.x * K2_WARPS) {
-    const int kind = row / rows0, r0 = row - kind * rows0;
-    const int b = r0 / g.F, f = r0 - b * g.F;
+    const int b = row / g.F, f = row - b * g.F;
     if (a.done != nullptr) {
       if (lane == 0) {
         const int* flag = a.done + b;
@@ -74,26 +72,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
       }
       __syncwarp();
     }
-    const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + ((size_t)kind * g.F + f) * g.SL;
-    if (kind > 0) {
-      // pooled bilinear form of the parameter gradients (training forward): assembled like p, tile order, no bias
-      float* qrow = a.q_out + (size_t)(kind - 1) * rows0 * g.n_count + (size_t)r0 * g.n_count;
-      for (int n = g.n_begin + lane; n < n_end; n += 32) {
-        int wlo = n * g.H - g.padL, whi = wlo + g.K - 1;
-        if (wlo < te_lo) wlo = te_lo;
-        if (whi > te_hi - 1) whi = te_hi - 1;
-        const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
-        float s = 0.f;
-        for (int i = i0; i <= i1; ++i) {
-          const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
-          int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
-          if (nf < g.n_begin) nf = g.n_begin;
-          s += __ldcg(pbase + (size_t)i * tile_stride + (n - nf));
-        }
-        qrow[n - g.n_begin] = s;
-      }
-      continue;
-    }
+    const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + (size_t)f * g.SL;
     const size_t ooff = (size_t)b * a.ldo_b + (size_t)f * a.ldo_f;
     float* orow = a.out + ooff;
     __nv_bfloat16* orow16 = reinterpret_cast<__nv_bfloat16*>(a.out) + ooff;
@@ -218,11 +197,44 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
   }
 }
 
+// Training forward: Q[kind-1][b][f][n] = sum over the tiles overlapping frame n of the partial sums of pooled quantity
+// `kind` (1..3: Q_mu, Q_sigma, Q_poolw; k1_tc.cu), in tile order.  One thread per output element, frames fastest:
+// nothing but index arithmetic and <= ceil(K/TL)+1 loads, so the kernel lives on memory-level parallelism (full
+// occupancy) -- as rows of the PCEN kernel (one warp per 100 frames, 59 registers) it took 0.44 ms at 1024 x 80 x 100.
+__global__ void __launch_bounds__(256)
+q_assemble_kernel(const Geom g, const float* __restrict__ ppart, float* __restrict__ q_out, int tl_shift,
+                  unsigned long long hop_magic) {
+  const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;
+  const long long per_kind = (long long)g.B * g.F * g.n_count, total = 3 * per_kind;
+  const size_t tile_stride = (size_t)4 * g.F * g.SL;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int kind = (int)(idx / per_kind) + 1;
+    const long long r = idx - (long long)(kind - 1) * per_kind;
+    const int nrel = (int)(r % g.n_count);
+    const long long bf = r / g.n_count;
+    const int b = (int)(bf / g.F), f = (int)(bf - (long long)b * g.F);
+    const int n = g.n_begin + nrel;
+    int wlo = n * g.H - g.padL, whi = wlo + g.K - 1;
+    if (wlo < te_lo) wlo = te_lo;
+    if (whi > te_hi - 1) whi = te_hi - 1;
+    const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
+    const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + ((size_t)kind * g.F + f) * g.SL;
+    float s = 0.f;
+    for (int i = i0; i <= i1; ++i) {
+      const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
+      int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
+      if (nf < g.n_begin) nf = g.n_begin;
+      s += __ldg(pbase + (size_t)i * tile_stride + (n - nf));
+    }
+    q_out[idx] = s;
+  }
+}
+
 cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cudaStream_t stream) {
   int tl_shift = 0;
   while ((1 << tl_shift) < g.TL) ++tl_shift;
   if ((1 << tl_shift) != g.TL) return cudaErrorInvalidValue;   // tile lengths are powers of two
-  const long long rows = (long long)g.B * g.F * (a.q_out != nullptr ? 4 : 1);
+  const long long rows = (long long)g.B * g.F;
   // long rows: one block per row (the choice depends on the frame count only, so a clip's features do not depend on
   // the batch it is in); else one warp per row.  Blocks beyond the resident wave are scheduled as earlier ones
   // retire (rows past the grid limit loop inside the kernel)
@@ -236,8 +248,16 @@ cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cuda
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = at; lc.numAttrs = 1;
-  if (rowblock) return cudaLaunchKernelEx(&lc, k2_pcen_kernel<true>, g, ppart, a, tl_shift, hop_magic);
-  return cudaLaunchKernelEx(&lc, k2_pcen_kernel<false>, g, ppart, a, tl_shift, hop_magic);
+  cudaError_t err = rowblock ? cudaLaunchKernelEx(&lc, k2_pcen_kernel<true>, g, ppart, a, tl_shift, hop_magic)
+                             : cudaLaunchKernelEx(&lc, k2_pcen_kernel<false>, g, ppart, a, tl_shift, hop_magic);
+  if (err != cudaSuccess || a.q_out == nullptr) return err;
+  // training forward: the three pooled bilinear forms, one thread per output element (after K2 in stream order, i.e.
+  // after the whole Gabor grid)
+  const long long total = 3LL * g.B * g.F * g.n_count;
+  long long qblocks = (total + 255) / 256;
+  if (qblocks > (1LL << 22)) qblocks = 1LL << 22;
+  q_assemble_kernel<<<(unsigned)qblocks, 256, 0, stream>>>(g, ppart, a.q_out, tl_shift, hop_magic);
+  return cudaGetLastError();
 }
 
 }  // namespace leafk
