@@ -10,7 +10,7 @@
 
 int main(void) {
   const int B = 4, T = 16000, F = 40;
-  leafk_config cfg = {F, 401, 160, 1e-12f, 1e-5f, 1, LEAFK_ALGO_AUTO, LEAFK_INPUT_F32};
+  leafk_config cfg = {F, 401, 160, 1e-12f, 1e-5f, 1, LEAFK_ALGO_AUTO, LEAFK_INPUT_F32, LEAFK_OUTPUT_F32, /*prep=*/NULL};
   const int N = leafk_num_frames(T, cfg.K, cfg.H);
   printf("libleafk version %d, %d frames per clip, tensor-core kernel %s\n", leafk_version(), N,
          leafk_tc_supported(F, cfg.K, cfg.H) ? "available" : "not used");
@@ -40,5 +40,25 @@ int main(void) {
   float* ho = (float*)malloc(sizeof(float) * B * F * N);
   cudaMemcpy(ho, out, sizeof(float) * B * F * N, cudaMemcpyDeviceToHost);
   printf("out[0,0,0..3] = %.6f %.6f %.6f %.6f\n", ho[0], ho[1], ho[2], ho[3]);
+
+  /* one training step: the training forward saves (p, Q_mu, Q_sigma, Q_poolw); the backward runs no correlation */
+  if (leafk_train_supported(F, cfg.K, cfg.H)) {
+    float *saved, *gout, *gpar;
+    void* tws; void* bws;
+    const size_t bfn = (size_t)B * F * N;
+    cudaMalloc((void**)&saved, sizeof(float) * 4 * bfn);
+    cudaMalloc((void**)&gout, sizeof(float) * bfn);
+    cudaMalloc((void**)&gpar, sizeof(float) * 8 * F);
+    for (size_t i = 0; i < bfn; ++i) ho[i] = 1.0f;                                   /* d(sum out)/d out */
+    cudaMemcpy(gout, ho, sizeof(float) * bfn, cudaMemcpyHostToDevice);
+    size_t tsz = leafk_train_workspace_bytes(&cfg, B, T), bsz = leafk_backward_saved_workspace_bytes(&cfg, B, T, 0);
+    cudaMalloc(&tws, tsz); cudaMalloc(&bws, bsz);
+    leafk_grads g = {gpar, gpar + 2 * F, gpar + 3 * F, gpar + 4 * F, gpar + 5 * F, gpar + 6 * F, gpar + 7 * F};
+    rc = leafk_forward_train(&cfg, &prm, x, B, T, out, saved, tws, tsz, NULL);
+    if (rc == LEAFK_OK) rc = leafk_backward_saved(&cfg, &prm, NULL, B, T, gout, saved, &g, NULL, bws, bsz, NULL);
+    if (rc != LEAFK_OK) { printf("training step failed: %s\n", leafk_last_error()); return 1; }
+    cudaMemcpy(hp, gpar, sizeof(float) * 8 * F, cudaMemcpyDeviceToHost);
+    printf("d(sum out)/d(centre, width) of filter 0 = %.6e %.6e\n", hp[0], hp[1]);
+  }
   return 0;
 }

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LEAFK_VERSION 100
+#define LEAFK_VERSION 200
 
 #define LEAFK_OK 0
 #define LEAFK_EINVAL (-1)     /* bad shape / null pointer / unsupported geometry            */
@@ -194,6 +194,8 @@ int leafk_backward_saved(const leafk_config* cfg, const leafk_params* prm, const
  * (stalled or failed H2D copy) makes the forward finish on whatever data is there and record the condition; this
  * call (a synchronous 4-byte read -- call it after synchronising the stream) returns LEAFK_ETIMEOUT then. */
 int leafk_async_status(const void* workspace);
+/* LEAFK_OK for word 0, else sets the thread's error message and returns LEAFK_ETIMEOUT (status_host words). */
+int leafk_status_message(int word);
 
 /* ---- the two stages the reference's constructor declares but does not implement (frontend.py:40-41, 62-63) -------
  * Stand-alone kernels around the fused frontend, forward and backward each; semantics of the original LEAF.
@@ -216,10 +218,13 @@ int leafk_instnorm_backward(const float* v, const float* stats, const float* gra
  * overlap without per-slice launch overheads; PCEN and the D2H copy follow on `stream`.  When
  * the FP32 kernel is selected, copy_stream == stream, or the driver lacks cuStreamWriteValue32,
  * it falls back to per-slice launches.  dev_x (B*T floats), dev_out (B*F*N floats) and workspace
- * are device scratch.  The call returns after enqueueing; the caller synchronises `stream`. */
+ * are device scratch.  The call returns after enqueueing; the caller synchronises `stream`.
+ * status_host (pinned host int, or NULL): receives the asynchronous error word together with the result (same stream
+ * order as out_host) -- 0, or a code for leafk_status_message(): no extra synchronisation is needed to learn that a
+ * slice of the copy stalled. */
 int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B,
                        int T, float* out_host, int n_slices, float* dev_x, float* dev_out,
-                       void* workspace, size_t workspace_bytes, void* stream, void* copy_stream);
+                       void* workspace, size_t workspace_bytes, void* stream, void* copy_stream, int* status_host);
 
 /* Fully asynchronous variant for serving loops that keep several batches in flight.  One call = one buffer SET
  * (dev_x, dev_out, workspace, the two events) -- use as many sets as batches in flight.  Ordering enforced
@@ -231,7 +236,7 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
 int leafk_forward_host_async(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B,
                              int T, float* out_host, int n_slices, float* dev_x, float* dev_out,
                              void* workspace, size_t workspace_bytes, void* stream, void* copy_stream,
-                             void* d2h_stream, void* ev_compute_done, void* ev_out_ready);
+                             void* d2h_stream, void* ev_compute_done, void* ev_out_ready, int* status_host);
 void* leafk_event_create(void);            /* cudaEvent_t without timing, or NULL */
 void leafk_event_destroy(void* ev);
 int leafk_event_synchronize(void* ev);

@@ -25,7 +25,7 @@ SYMBOLS = (
     "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end", "leafk_profile_k1_clock", "leafk_profile_tc_schedule",
     "leafk_forward_host_async", "leafk_event_create", "leafk_event_destroy", "leafk_event_synchronize",
     "leafk_train_supported", "leafk_train_workspace_bytes", "leafk_forward_train", "leafk_backward_saved",
-    "leafk_backward_saved_workspace_bytes", "leafk_async_status", "leafk_peak_divisors",
+    "leafk_backward_saved_workspace_bytes", "leafk_async_status", "leafk_status_message", "leafk_peak_divisors",
     "leafk_preemp_forward", "leafk_preemp_backward", "leafk_preemp_backward_workspace_bytes", "leafk_instnorm_forward",
     "leafk_instnorm_backward",
 )
@@ -93,7 +93,7 @@ def lib() -> C.CDLL:
         L.leafk_backward_workspace_bytes.argtypes = [C.POINTER(Config), i, i]
         L.leafk_forward_host.restype = i
         L.leafk_forward_host.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, i, vp, vp, vp, sz,
-                                         vp, vp]
+                                         vp, vp, vp]
         L.leafk_tc_supported.restype = i
         L.leafk_tc_supported.argtypes = [i, i, i]
         L.leafk_profile_begin.restype = None
@@ -107,7 +107,7 @@ def lib() -> C.CDLL:
                                                 C.POINTER(i), i]
         L.leafk_forward_host_async.restype = i
         L.leafk_forward_host_async.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, i, vp, vp, vp, sz,
-                                               vp, vp, vp, vp, vp]
+                                               vp, vp, vp, vp, vp, vp]
         L.leafk_event_create.restype = vp
         L.leafk_event_create.argtypes = []
         L.leafk_event_destroy.restype = None
@@ -139,6 +139,8 @@ def lib() -> C.CDLL:
         L.leafk_instnorm_backward.argtypes = [vp, vp, vp, ll, i, vp, vp]
         L.leafk_async_status.restype = i
         L.leafk_async_status.argtypes = [vp]
+        L.leafk_status_message.restype = i
+        L.leafk_status_message.argtypes = [i]
         L.leafk_launch_count.restype = ll
         L.leafk_launch_count.argtypes = [i]
         _lib = L

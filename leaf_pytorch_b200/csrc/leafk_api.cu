@@ -364,7 +364,7 @@ static int forward_host_sliced(const leafk_config* cfg, const leafk_params* prm,
 
 int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B, int T,
                        float* out_host, int n_slices, float* dev_x, float* dev_out, void* workspace,
-                       size_t workspace_bytes, void* stream_, void* copy_stream_) {
+                       size_t workspace_bytes, void* stream_, void* copy_stream_, int* status_host) {
   if (!cfg || !prm || !x_host || !out_host || !dev_x || !dev_out || !workspace)
     return fail(LEAFK_EINVAL, "null pointer argument");
   if (cfg->prep) return fail(LEAFK_EINVAL, "host-buffer calls take prepared batches (cfg->prep must be NULL)");
@@ -380,8 +380,11 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
   if (rc) return rc;
   StreamWriteValue32Fn write32 = stream_write_value32();
   if (algo != LEAFK_ALGO_TC || cstream == stream || write32 == nullptr || n_slices == 1)
+  {
+    if (status_host != nullptr) *status_host = 0;      // no flags on this path: nothing can time out
     return forward_host_sliced(cfg, prm, x_host, B, T, N, out_host, n_slices > 16 ? 16 : n_slices, dev_x, dev_out,
                                workspace, workspace_bytes, stream, cstream);
+  }
 
   // Pipelined path: ONE persistent launch of the tensor-core kernel over the whole batch; its producers wait
   // per clip on slice-ready flags that follow each slice of the H2D copy in copy_stream order.
@@ -408,6 +411,10 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
   if (rc) return rc;
   e = cudaMemcpyAsync(out_host, dev_out, sizeof(float) * (size_t)B * cfg->F * N, cudaMemcpyDeviceToHost, stream);
   if (e != cudaSuccess) return fail(LEAFK_ECUDA, "D2H: %s", cudaGetErrorString(e));
+  if (status_host != nullptr) {                         // the asynchronous error word travels with the result
+    e = cudaMemcpyAsync(status_host, workspace, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) return fail(LEAFK_ECUDA, "status D2H: %s", cudaGetErrorString(e));
+  }
   return LEAFK_OK;
 }
 
@@ -426,7 +433,7 @@ int leafk_event_synchronize(void* ev) {
 int leafk_forward_host_async(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B, int T,
                              float* out_host, int n_slices, float* dev_x, float* dev_out, void* workspace,
                              size_t workspace_bytes, void* stream_, void* copy_stream_, void* d2h_stream_,
-                             void* ev_compute_done_, void* ev_out_ready_) {
+                             void* ev_compute_done_, void* ev_out_ready_, int* status_host) {
   if (!cfg || !prm || !x_host || !out_host || !dev_x || !dev_out || !workspace || !ev_compute_done_ || !ev_out_ready_)
     return fail(LEAFK_EINVAL, "null pointer argument");
   if (cfg->prep) return fail(LEAFK_EINVAL, "host-buffer calls take prepared batches (cfg->prep must be NULL)");
@@ -475,6 +482,10 @@ int leafk_forward_host_async(const leafk_config* cfg, const leafk_params* prm, c
   cudaStreamWaitEvent(dstream, ev_compute_done, 0);
   e = cudaMemcpyAsync(out_host, dev_out, sizeof(float) * (size_t)B * cfg->F * N, cudaMemcpyDeviceToHost, dstream);
   if (e != cudaSuccess) return fail(LEAFK_ECUDA, "D2H: %s", cudaGetErrorString(e));
+  if (status_host != nullptr) {                         // the asynchronous error word travels with the result
+    e = cudaMemcpyAsync(status_host, workspace, sizeof(int), cudaMemcpyDeviceToHost, dstream);
+    if (e != cudaSuccess) return fail(LEAFK_ECUDA, "status D2H: %s", cudaGetErrorString(e));
+  }
   cudaEventRecord(ev_out_ready, dstream);
   return LEAFK_OK;
 }
@@ -503,6 +514,10 @@ int leafk_async_status(const void* workspace) {
   int word = 0;
   cudaError_t e = cudaMemcpy(&word, workspace, sizeof(int), cudaMemcpyDeviceToHost);   // synchronous by design
   if (e != cudaSuccess) return fail(LEAFK_ECUDA, "status read: %s", cudaGetErrorString(e));
+  return leafk_status_message(word);
+}
+
+int leafk_status_message(int word) {
   if (word == LEAFK_ASYNC_H2D_TIMEOUT)
     return fail(LEAFK_ETIMEOUT, "a slice of the host-to-device copy never signalled ready (stalled copy); features invalid");
   if (word == LEAFK_ASYNC_K1_TIMEOUT)

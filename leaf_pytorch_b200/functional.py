@@ -469,18 +469,20 @@ def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, a
                     _host_cache.pop(next(iter(_host_cache)))
                 bufs = (torch.empty(B * T, dtype=x_host.dtype, device=device),
                         torch.empty(B * spec.F * n, dtype=torch.float32, device=device),
-                        torch.empty(ws_bytes, dtype=torch.uint8, device=device), torch.cuda.Stream(device=device))
+                        torch.empty(ws_bytes, dtype=torch.uint8, device=device), torch.cuda.Stream(device=device),
+                        torch.zeros(1, dtype=torch.int32).pin_memory())
                 _host_cache[key] = bufs
-        dev_x, dev_out, ws, side = bufs
+        dev_x, dev_out, ws, side, status = bufs
         cur = torch.cuda.current_stream(device)
         side.wait_stream(cur)
         rc = L.leafk_forward_host(C.byref(cfg), C.byref(prm), C.c_void_p(x_host.data_ptr()), B, T,
                                   C.c_void_p(out_host.data_ptr()), int(n_slices), _ptr(dev_x), _ptr(dev_out),
-                                  _ptr(ws), ws.numel(), C.c_void_p(cur.cuda_stream), C.c_void_p(side.cuda_stream))
+                                  _ptr(ws), ws.numel(), C.c_void_p(cur.cuda_stream), C.c_void_p(side.cuda_stream),
+                                  C.c_void_p(status.data_ptr()))
         N.check(rc, "leafk_forward_host")
         cur.synchronize()
-        # a stalled H2D slice is reported here instead of trapping inside the kernel
-        N.check(L.leafk_async_status(_ptr(ws)), "leafk_forward_host")
+        # a stalled H2D slice is reported here (the status word came back with the features) instead of a trap in the kernel
+        N.check(L.leafk_status_message(int(status[0])), "leafk_forward_host")
     del keep
     return out_host
 

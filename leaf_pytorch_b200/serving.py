@@ -23,7 +23,7 @@ from . import functional as LF
 
 
 class _Set:
-    __slots__ = ("dev_x", "dev_out", "ws", "ev_compute", "ev_out", "out_host", "busy", "keep", "ticket")
+    __slots__ = ("dev_x", "dev_out", "ws", "ev_compute", "ev_out", "out_host", "busy", "keep", "ticket", "status")
 
 
 class HostPipeline:
@@ -57,6 +57,7 @@ class HostPipeline:
                 s.ev_out = self.lib.leafk_event_create()
                 if not s.ev_compute or not s.ev_out:
                     raise N.LeafNativeError("could not create CUDA events")
+                s.status = torch.zeros(1, dtype=torch.int32).pin_memory()       # asynchronous error word, arrives with the result
                 s.out_host, s.busy, s.keep, s.ticket = None, False, None, -1
                 self.sets.append(s)
         self._next = 0                    # monotonically increasing ticket of the next batch
@@ -86,7 +87,8 @@ class HostPipeline:
                 C.c_void_p(out_host.data_ptr()), int(self.n_slices), C.c_void_p(s.dev_x.data_ptr()),
                 C.c_void_p(s.dev_out.data_ptr()), C.c_void_p(s.ws.data_ptr()), s.ws.numel(),
                 C.c_void_p(self.compute_stream.cuda_stream), C.c_void_p(self.copy_stream.cuda_stream),
-                C.c_void_p(self.d2h_stream.cuda_stream), C.c_void_p(s.ev_compute), C.c_void_p(s.ev_out))
+                C.c_void_p(self.d2h_stream.cuda_stream), C.c_void_p(s.ev_compute), C.c_void_p(s.ev_out),
+                C.c_void_p(s.status.data_ptr()))
         N.check(rc, "leafk_forward_host_async")
         s.out_host, s.busy, s.keep, s.ticket = out_host, True, (keep, x_host), ticket
         return ticket
@@ -94,8 +96,9 @@ class HostPipeline:
     def _collect(self, s: _Set) -> torch.Tensor:
         N.check(self.lib.leafk_event_synchronize(C.c_void_p(s.ev_out)), "leafk_event_synchronize")
         s.busy, s.keep = False, None
-        # a stalled host-to-device slice is reported here (the kernels record it instead of trapping)
-        N.check(self.lib.leafk_async_status(C.c_void_p(s.ws.data_ptr())), "leafk_forward_host_async")
+        # a stalled host-to-device slice is reported here (the kernels record it instead of trapping; the word was copied
+        # back right behind the features, so reading it costs nothing)
+        N.check(self.lib.leafk_status_message(int(s.status[0])), "leafk_forward_host_async")
         return s.out_host
 
     def result(self, ticket: int) -> torch.Tensor:

@@ -118,7 +118,7 @@ def test_c_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, sym), f"{sym} declared in include/leafk.h but not exported"
     assert set(_native.SYMBOLS) <= declared
     L_ = _native.lib()
-    assert L_.leafk_version() == 100
+    assert L_.leafk_version() == 200
     assert L_.leafk_num_frames(16000, 401, 160) == 100
     lo, hi = ctypes.c_int(), ctypes.c_int()
     L_.leafk_same_padding(552, ctypes.byref(lo), ctypes.byref(hi))
@@ -198,7 +198,7 @@ def test_plain_c_client_compiles_links_and_runs_host_calls(tmp_path):
                     "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64",
                     "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
-    assert "libleafk version 100, 100 frames per clip" in out
+    assert "libleafk version 200, 100 frames per clip" in out
 
 
 @pytest.mark.reference
