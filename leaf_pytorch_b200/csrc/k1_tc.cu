@@ -35,9 +35,9 @@
 // Accumulators rotate through NST = 512/NB tensor-memory stages so the epilogue of phase p overlaps
 // the MMAs of phases p+1.. .  The bank of the CTA's channel group stays resident in shared memory.
 // The kernel is chained to k0 (before) and k2 (after) by programmatic dependent launch.
-// Registers: the CTA launches with 168 per thread; warps 8-11 (MMA issuer + producers) give theirs back
-// (setmaxnreg.dec) and the two epilogue warpgroups take them (setmaxnreg.inc), so the accumulator-heavy epilogues
-// do not spill.
+// Registers: the CTA launches with 168 per thread; warps 8-11 (MMA issuer + producers) give some back
+// (setmaxnreg.dec to 136) and the two epilogue warpgroups take them (setmaxnreg.inc to 184), so the accumulator-heavy
+// epilogues (up to 96 accumulators per thread in training) do not spill.
 //
 // MODE 1 = TRAINING forward (Leaf.forward when parameters require grad).  Besides y it runs the two derivative
 // banks z = x*(tau h), v = x*((tau^2/sigma^3 - 1/sigma) h) ("equivalent without forming dW") and pools,
@@ -483,7 +483,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
 
   if (warp >= MMA_WARP) {
     // ---- warpgroup 2: MMA issuer (warp 8) + producers (warps 9-11): give registers to the epilogue warpgroups
-    if (cpt <= 2) setmaxnreg_dec<104>(); else setmaxnreg_dec<152>();
+    if (cpt <= 2) setmaxnreg_dec<136>(); else setmaxnreg_dec<152>();
     if (warp >= PROD_WARP0) {
       // =========================================== PRODUCERS ======================================
       if (cpt <= 2)
@@ -585,7 +585,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
     }
   } else {
     // =========================================== EPILOGUE =========================================
-    if (cpt <= 2) setmaxnreg_inc<200>(); else setmaxnreg_inc<176>();
+    if (cpt <= 2) setmaxnreg_inc<184>(); else setmaxnreg_inc<176>();
     const int e = warp, q = e & 3, hh = e >> 2;
     const int etid = tid;                               // 0..255
     const int m = 32 * q + lane;                        // accumulator row

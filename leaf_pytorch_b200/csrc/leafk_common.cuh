@@ -46,7 +46,7 @@ struct Geom {
 // What a kernel needs to read clip b: row offset, crop start, raw length, divisor.
 struct ClipView {
   size_t row;
-  long long start, len;
+  int start, len;          // clip lengths are below 2^30 (checked on the host), crop offsets within +-2^29
   float div;
   bool prep;
 };
@@ -63,7 +63,7 @@ __device__ __forceinline__ ClipView clip_view(const Geom& g, int b) {
   v.row = (size_t)b * g.ldx;
   v.prep = g.clip_start != nullptr || g.clip_len != nullptr || g.clip_div != nullptr;
   v.start = g.clip_start ? g.clip_start[b] : 0;
-  v.len = g.clip_len ? g.clip_len[b] : g.T_total;
+  v.len = g.clip_len ? g.clip_len[b] : (int)g.T_total;
   v.div = g.clip_div ? g.clip_div[b] : 1.0f;
   return v;
 }
@@ -71,7 +71,7 @@ __device__ __forceinline__ ClipView clip_view(const Geom& g, int b) {
 // the sample lies inside [0, T_total)
 __device__ __forceinline__ float clip_sample(const Geom& g, const float* x, const ClipView& v, long long wi) {
   if (!v.prep) return load_sample(x, v.row, wi, g.x_fmt);
-  long long j = g.t_off + wi + v.start;
+  int j = (int)(g.t_off + wi) + v.start;
   if (j < 0 || j >= v.len) {
     if (!g.clip_wrap || v.len <= 0) return 0.f;
     j %= v.len;
