@@ -430,20 +430,25 @@ def main():
                 up_done[i % 2].record(copy_s)
 
         def e2e_loop_generic(n):
+            ring = [None, None, None]          # results stay alive until their read-back has finished (no allocator churn)
+            d2h_done = [torch.cuda.Event() for _ in range(3)]
             upload(0)
             for i in range(n):
                 if i + 1 < n:
                     upload(i + 1)
                 cur_s.wait_event(up_done[i % 2])
+                if ring[i % 3] is not None:
+                    cur_s.wait_event(d2h_done[i % 3])    # the buffer about to be released has been read back
                 out = step(dbuf[i % 2])
                 used[i % 2].record(cur_s)
                 res = torch.cat([p.grad.reshape(-1) for p in params]) if mode == "train" else out
+                ring[i % 3] = res
                 d2h_s.wait_stream(cur_s)                 # the read-back overlaps the next step
                 with torch.cuda.stream(d2h_s):
                     res_host.copy_(res, non_blocking=True)
-                    res.record_stream(d2h_s)
+                    d2h_done[i % 3].record(d2h_s)
             torch.cuda.synchronize()
-        e2e_loop_generic(2)
+        e2e_loop_generic(4)
         barrier()
         t_start = time.perf_counter()
         e2e_loop_generic(steps)

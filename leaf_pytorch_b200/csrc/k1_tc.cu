@@ -377,6 +377,7 @@ __device__ __forceinline__ void tile_end_rowsums(const float (&acc)[NV][NSLOT], 
     }
   } else {
     // generic geometry (more frames per warp): row sums through the transpose buffer, one frame at a time
+    if (red == nullptr) __trap();                       // lean plan: the host admits only geometries that never get here
     if (nb_hi > n_last) nb_hi = n_last;
     for (int n = nb_lo; n <= nb_hi; ++n) {
       const int slot = n - n_first;
@@ -591,7 +592,8 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
     const int m = 32 * q + lane;                        // accumulator row
     const float centre = 0.5f * (float)(g.K - 1);
     const int n_last = g.n_begin + g.n_count - 1;
-    float* red = s_red + (size_t)e * NV * 33;           // this warp's transpose buffer (generic tile-end row sums)
+    constexpr bool LEAN = lean_plan(CG, MODE);
+    float* red = LEAN ? nullptr : s_red + (size_t)e * NV * 33;   // this warp's transpose buffer (generic tile-end row sums)
     int sig_b = -1;                                     // clip whose last stored tile K2 has not been told about yet
     const int FV = (MODE == 0) ? g.F : 4 * g.F;         // virtual filters per (clip, tile) block of partial sums
 
@@ -670,15 +672,19 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + hh * (CG / 2));
         if constexpr (MODE == 0) {
           const uint32_t tlo = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(st * NB + 2 * CG - 8 - hh * (CG / 2));
+          // software-pipelined tensor-memory loads: chunk c+1 is in flight while chunk c is processed
+          uint32_t bm[2][8], bc[2][8];
+          tmem_ld8x2_issue(taddr, tlo, bm[0], bc[0]);
 #pragma unroll
           for (int c = 0; c < NV / 4; ++c) {
             // hi products of the 4 filters at columns hh*CG/2 + 8c ..; their lo products sit in the mirrored
             // 8-column block of the lo half, filters in reverse order (k1_tc_layout.cuh)
-            float ym[8], yc[8];
-            tmem_ld8x2_sync(taddr + 8 * c, tlo - 8 * c, ym, yc);
+            tmem_ld_wait(bm[c & 1], bc[c & 1]);
+            if (c + 1 < NV / 4) tmem_ld8x2_issue(taddr + 8 * (c + 1), tlo - 8 * (c + 1), bm[(c + 1) & 1], bc[(c + 1) & 1]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float re = ym[2 * i] + yc[2 * (3 - i)], im = ym[2 * i + 1] + yc[2 * (3 - i) + 1];
+              const float re = __uint_as_float(bm[c & 1][2 * i]) + __uint_as_float(bc[c & 1][2 * (3 - i)]);
+              const float im = __uint_as_float(bm[c & 1][2 * i + 1]) + __uint_as_float(bc[c & 1][2 * (3 - i) + 1]);
               const float en = fmaf(re, re, im * im);
 #pragma unroll
               for (int j = 0; j < NSLOT; ++j)
@@ -690,18 +696,27 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
           float dv[NSLOT];                                // (k - c)^2 inside the window, 0 outside
 #pragma unroll
           for (int j = 0; j < NSLOT; ++j) dv[j] = dj[j] < 1.0e29f ? dj[j] : 0.f;
+          // y, z, v accumulators (all three split products already summed in tensor memory) of 4 filters per chunk;
+          // chunk c+1 is in flight while chunk c is processed
+          uint32_t by[2][8], bz[2][8], bv[2][8];
+          tmem_ld8_issue(taddr, by[0]); tmem_ld8_issue(taddr + FB, bz[0]); tmem_ld8_issue(taddr + 2 * FB, bv[0]);
 #pragma unroll
           for (int c = 0; c < NF / 4; ++c) {
-            // y, z, v accumulators (all three split products already summed in tensor memory) of 4 filters
-            float yv[8], zv[8], vv[8];
-            tmem_ld8x3_sync(taddr + 8 * c, taddr + FB + 8 * c, taddr + 2 * FB + 8 * c, yv, zv, vv);
+            tmem_ld_wait(by[c & 1], bz[c & 1], bv[c & 1]);
+            if (c + 1 < NF / 4) {
+              tmem_ld8_issue(taddr + 8 * (c + 1), by[(c + 1) & 1]);
+              tmem_ld8_issue(taddr + FB + 8 * (c + 1), bz[(c + 1) & 1]);
+              tmem_ld8_issue(taddr + 2 * FB + 8 * (c + 1), bv[(c + 1) & 1]);
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int fi = 4 * c + i;
-              const float yre = yv[2 * i], yim = yv[2 * i + 1];
+              const float yre = __uint_as_float(by[c & 1][2 * i]), yim = __uint_as_float(by[c & 1][2 * i + 1]);
+              const float zre = __uint_as_float(bz[c & 1][2 * i]), zim = __uint_as_float(bz[c & 1][2 * i + 1]);
+              const float vre = __uint_as_float(bv[c & 1][2 * i]), vim = __uint_as_float(bv[c & 1][2 * i + 1]);
               const float en = fmaf(yre, yre, yim * yim);
-              const float qm = fmaf(yim, zv[2 * i], -(yre * zv[2 * i + 1]));
-              const float qs = fmaf(yre, vv[2 * i], yim * vv[2 * i + 1]);
+              const float qm = fmaf(yim, zre, -(yre * zim));
+              const float qs = fmaf(yre, vre, yim * vim);
 #pragma unroll
               for (int j = 0; j < NSLOT; ++j) {
                 const float wgt = ex2_approx(pa[fi] * dj[j]);
@@ -725,7 +740,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       }
 
       // ---- tile end: row sums of this warp -> s_pw[buf][e][slot][vi], then the quadrant sum and the store --------
-      float* pw_buf = s_pw + (size_t)(it & 1) * (EPI_WARPS * g.SL * NV);
+      float* pw_buf = s_pw + (LEAN ? (size_t)0 : (size_t)(it & 1) * (EPI_WARPS * g.SL * NV));
       tile_end_rowsums<NV, NSLOT>(acc, pw_buf + (size_t)e * g.SL * NV, red, lane, nb, n_first, n_last, g.SL);
       named_bar_sync(BAR_EPI, EPI_WARPS * 32);
       const int sx = misc->sx_ring[it & 3];
@@ -756,7 +771,7 @@ bool k1_tc_supported(const Geom& g, const char** why) {
   if (nslot > 5) { if (why) *why = "hop too small relative to the window (more than 5 frames per 8 samples)"; return false; }
   if (g.Kp > 2048) { if (why) *why = "window longer than 2048 taps"; return false; }
   int ng, cg;
-  if (!tc::channel_groups(g.C2, g.Kp, g.SL, nslot, &ng, &cg)) {
+  if (!tc::channel_groups(g.C2, g.Kp, g.SL, nslot, &ng, &cg, g.K, g.H)) {
     if (why) *why = "shared-memory plan does not fit for any channel grouping";
     return false;
   }
@@ -860,6 +875,8 @@ cudaError_t launch_k1_tc(const Geom& g, const float* x, const uint8_t* w16, cons
     case 64: return launch_cg<64>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
     case 80: return launch_cg<80>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
     case 96: return launch_cg<96>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
+    case 112: return launch_cg<112>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
+    case 128: return launch_cg<128>(nslot, g, x, w16, cprm, ppart, tc_groups, grid, smem, stream, rdy, tm);
     default: return cudaErrorNotSupported;
   }
 }

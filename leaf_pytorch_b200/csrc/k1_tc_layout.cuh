@@ -57,7 +57,8 @@ namespace tc {
 constexpr int KSTEP = 16;            // taps per MMA (kind::f16, K = 16)
 constexpr int TILE = 1024;           // e-samples per tile: 128 MMA rows x 8 phases
 constexpr int NPHASE = 8;
-constexpr int MAX_CG = 96;           // largest channel group instantiated (NB = 192 accumulator columns)
+constexpr int MAX_CG = 128;          // largest channel group instantiated (NB = 256 accumulator columns, 2 stages)
+constexpr int MAX_CG_FULL = 96;      // largest group with the full shared-memory plan (see lean_plan)
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 __host__ __device__ inline size_t region_offset(int R, int n, int k) {
@@ -138,6 +139,14 @@ struct SmemPlan {
 // (e, q_mu, q_sigma, q_poolw), FB = CG/6 filters per group.
 __host__ __device__ constexpr int virt_per_thread(int CG, int mode) { return mode == 0 ? CG / 4 : 4 * (CG / 12); }
 
+// Channel groups above 96 channels (F = 49..64 as ONE group: the A copies are built once per tile instead of twice and
+// the pruned MMAs stay above the 39-cycle A-fetch floor) only fit the 227 KB with a LEAN plan: a single buffer of
+// per-warp row sums (safe: with <= 4 accumulator stages no epilogue warp can run a whole tile ahead of another) and no
+// transpose buffer for the generic tile-end path -- so they need the fast tile-end path on every tile:
+// ceil(248 / H) + NSLOT - 1 < NSLOT + 2, i.e. H >= 124, and NSLOT = 3.
+__host__ __device__ constexpr bool lean_plan(int CG, int mode) { return mode == 0 && CG > MAX_CG_FULL; }
+__host__ __device__ inline bool lean_geometry_ok(int K, int H) { return H >= 124 && (K + 6) / H + 1 <= 3; }
+
 // mode 0: forward, mode 1: training forward (banks h, tau*h, (tau^2/sigma^3 - 1/sigma)*h; see "TRAINING LAYOUT")
 __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode = 0, int nslot = 3) {
   SmemPlan s;
@@ -148,12 +157,13 @@ __host__ __device__ inline SmemPlan smem_plan(int CG, int Kp, int SL, int mode =
   int off = 0;
   s.off_w = off;      off += (mode == 0) ? (int)b_cta_bytes(CG, Kp) : (int)t_cta_bytes(CG, Kp);
   s.off_acopy = off;  off += 16 * s.acb;
-  s.off_pw = off;     off += 2 * 8 * SL * NV * 4;          // two buffers of per-warp row sums [8 warps][SL][NV]
+  const bool lean = lean_plan(CG, mode);
+  s.off_pw = off;     off += (lean ? 1 : 2) * 8 * SL * NV * 4;   // buffers of per-warp row sums [8 warps][SL][NV]
   // per epilogue warp an NV x 33 float transpose buffer (generic tile-end row sums)
   s.off_red = (off + 15) / 16 * 16;
   // per (virtual filter, slot) output of a tile {offset in the reduction buffer, offset in the tile's partial-sum
   // block or -1, power-of-two exponent of the bank scaling, 0}: tile independent, built once per CTA
-  s.off_out = s.off_red + 8 * NV * 33 * 4;
+  s.off_out = s.off_red + (lean ? 0 : 8 * NV * 33 * 4);
   s.off_out = (s.off_out + 15) / 16 * 16;
   s.off_misc = s.off_out + SL * (2 * NV) * 16;
   s.off_misc = (s.off_misc + 15) / 16 * 16;
@@ -176,12 +186,13 @@ __host__ __device__ inline int slots_per_thread(int K, int H) { return (K + 6) /
 
 // Split C2 channels into the fewest groups of CG channels (CG a multiple of 16, <= MAX_CG) whose
 // shared-memory plan fits.  Returns false when no group size fits.
-__host__ __device__ inline bool channel_groups(int C2, int Kp, int SL, int nslot, int* n_groups, int* CG) {
+__host__ __device__ inline bool channel_groups(int C2, int Kp, int SL, int nslot, int* n_groups, int* CG, int K = 0, int H = 0) {
   const int max_cg = nslot > 3 ? 64 : MAX_CG;
   for (int g = 1; g <= 64; ++g) {
     int cg = (C2 + g - 1) / g;
     cg = (cg + 15) / 16 * 16;
     if (cg > max_cg) continue;
+    if (cg > MAX_CG_FULL && !(K > 0 && lean_geometry_ok(K, H))) continue;
     if (smem_plan(cg, Kp, SL, 0, nslot > 3 ? 5 : 3).total > SMEM_LIMIT) continue;
     *n_groups = (C2 + cg - 1) / cg;
     *CG = cg;

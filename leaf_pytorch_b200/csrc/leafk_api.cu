@@ -124,7 +124,7 @@ static int make_geom(const leafk_config* cfg, int B, long long ldx, long long T_
 
 static void carve(const Geom& g, int max_tiles_fp32, int max_tiles_tc, Workspace* w, int* tc_cg, int* tc_groups) {
   const int sl_tc = (TC_TILE + g.K - 2) / g.H + 1;
-  tc::channel_groups(g.C2, g.Kp, sl_tc, tc::slots_per_thread(g.K, g.H), tc_groups, tc_cg);
+  tc::channel_groups(g.C2, g.Kp, sl_tc, tc::slots_per_thread(g.K, g.H), tc_groups, tc_cg, g.K, g.H);
   size_t off = 0;
   // first, so that its address does not depend on the shapes: 16 ints (int 0 = asynchronous error word), then the
   // per-clip completion counters

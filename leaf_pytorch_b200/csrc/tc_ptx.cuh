@@ -241,6 +241,41 @@ __device__ __forceinline__ void tmem_ld8x2_sync(uint32_t taddr_a, uint32_t taddr
 #pragma unroll
   for (int i = 0; i < 8; ++i) { va[i] = __uint_as_float(a[i]); vb[i] = __uint_as_float(b[i]); }
 }
+// Split load / wait for software pipelining: tcgen05.wait::ld waits for every load the thread has issued so far, so
+// the epilogue waits for chunk c, THEN issues chunk c+1 into the other register set, and computes on chunk c while
+// c+1 is in flight.  The wait takes the registers as in/out operands so that no use can be scheduled ahead of it.
+__device__ __forceinline__ void tmem_ld8x2_issue(uint32_t taddr_a, uint32_t taddr_b, uint32_t (&a)[8], uint32_t (&b)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(b[0]),
+        "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7])
+      : "r"(taddr_a), "r"(taddr_b)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&a)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[8], uint32_t (&b)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(b[0]),
+                 "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&a)[8], uint32_t (&b)[8], uint32_t (&c)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(b[0]),
+                 "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(c[0]), "+r"(c[1]),
+                 "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7])
+               :
+               : "memory");
+}
+
 // three 8-column loads (y, z, v accumulators of 4 filters), one wait
 __device__ __forceinline__ void tmem_ld8x3_sync(uint32_t ta, uint32_t tb, uint32_t tc_, float* va, float* vb, float* vc) {
   uint32_t a[8], b[8], c[8];
