@@ -730,7 +730,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_rank0(&misc->acc_empty[st]);
+        if (lane == 0) mbar_arrive_rank0_relaxed(&misc->acc_empty[st]);   // no memory published: TMEM reads are complete
         if (p == 1 && sig_b >= 0) {          // the previous tile's partial sums were stored a phase ago: publish them to K2
           __threadfence();
           __syncwarp();

@@ -77,6 +77,18 @@ __device__ __forceinline__ void mbar_arrive_rank0(uint64_t* bar) {
       ::"r"(smem_u32(bar))
       : "memory");
 }
+// Same without memory ordering: for hand-offs that publish no memory -- the epilogue telling the MMA issuer that it has
+// finished READING an accumulator stage (tcgen05.wait::ld has completed the reads; tcgen05.fence::before_thread_sync
+// orders them before the arrive).  The release.cluster form costs a MEMBAR.ALL.GPU + ERRBAR per arrive (~2000 of 17000
+// epilogue stall samples at cfg2, ncu source page).
+__device__ __forceinline__ void mbar_arrive_rank0_relaxed(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
 // wait with cluster-scope acquire (arrivals may come from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   for (uint32_t spins = 0;; ++spins) {

@@ -119,3 +119,41 @@ def test_training_forward_output_equals_inference_forward():
     assert d < 5e-6, d
     fe.requires_grad_(False)
     assert fe(x.cuda()).grad_fn is None
+
+
+def test_c_abi_leafk_backward_from_waveform_and_saved_energies():
+    """include/leafk.h leafk_backward: gradients from x + the pooled energies saved by leafk_forward only (the entry
+    point a non-PyTorch host would call).  On a tensor-core geometry it re-runs the training forward inside its
+    workspace; the result must equal what the autograd path (leafk_forward_train + leafk_backward_saved) gives."""
+    import ctypes as C
+    import leaf_pytorch_b200.functional as LF
+    from leaf_pytorch_b200 import _native as N
+    case, x, prm, z = load_golden("grad_default")
+    fe = build(case, prm, "auto")
+    xd = x.cuda()
+    G = torch.from_numpy(make_grad_out(z["out"].shape, case.seed)).cuda()
+    (fe(xd) * G).sum().backward()
+    want = [p.grad.detach().reshape(-1).clone() for p in fe._param_tuple()]
+    # the same through the raw C ABI
+    L = N.lib()
+    spec = fe.spec
+    prm_t = [p.detach() for p in fe._param_tuple()]
+    out, saved_p = LF.forward_raw(spec, xd, *prm_t, save_p=True)
+    cfg = spec.config(xd.dtype)
+    ps, keep = LF._params_struct(spec, *prm_t, xd.device)
+    grads_t = [torch.empty(p.numel(), device="cuda") for p in prm_t]
+    gs = N.Grads(*[g.data_ptr() for g in grads_t])
+    B, _, T = xd.shape
+    gx = torch.empty_like(xd)
+    nbytes = L.leafk_backward_workspace_bytes(C.byref(cfg), B, T)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    rc = L.leafk_backward(C.byref(cfg), C.byref(ps), C.c_void_p(xd.data_ptr()), B, T, C.c_void_p(G.data_ptr()),
+                          C.c_void_p(saved_p.data_ptr()), C.byref(gs), C.c_void_p(gx.data_ptr()), C.c_void_p(ws.data_ptr()),
+                          nbytes, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    N.check(rc, "leafk_backward")
+    torch.cuda.synchronize()
+    for got, w in zip(grads_t, want):
+        assert scaled_err(got.cpu().numpy(), w.cpu().numpy()) < 1e-6
+    from oracle import leaf_oracle as O
+    ref = O.grads_f32(x, prm, case.K, case.H, G.cpu(), with_input=True)
+    assert scaled_err(gx.cpu().numpy().reshape(-1), ref["x"].numpy().reshape(-1)) < 1e-3

@@ -235,6 +235,22 @@ def test_bench_reference_arm_prints_contract_json():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
     assert "workload" in line["config"] and line["vs_baseline"] is None
+    # both arms print the SAME config object for the same --config / world size (the driver compares them key by key)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.workload_config(2, 1)
+    assert set(bench.CONFIGS) == {1, 2, 3, 4, 5}
+
+
+def test_bench_reference_arm_training_config():
+    """--impl reference --config 3: forward + backward of the CPU port on a stated sample of the workload's clips."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "3", "--steps", "1",
+                          "--warmup", "1"], check=True, capture_output=True, text=True, timeout=600).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["config"]["config_id"] == 3 and line["config"]["pass"] == "train"
+    assert line["step_clips"] == 8 and "forward+backward" in line["cpu_baseline"]["sample"] and line["value"] > 0
 
 
 def test_header_constants_match_the_python_binding():

@@ -116,3 +116,39 @@ def test_needed_samples_is_exactly_the_dependency_window():
             z[..., edge] += 1.0
             outz = O.forward_f64(z, prm, K, H, compression=False)
             assert not torch.equal(outz[..., n0:n0 + cnt], base[..., n0:n0 + cnt])
+
+
+def test_prepare_clip_restates_the_reference_transforms():
+    """oracle.prepare_clip against numpy / torch one-liners of the reference's per-clip transforms
+    (utilities/data/raw_transforms.py:121-160, 334-344): pad (wrap / zero), centre or offset crop, peak normalisation
+    only when the peak exceeds 1."""
+    import numpy as np
+    import torch
+    from oracle import leaf_oracle as O
+    rng = np.random.default_rng(0)
+    long = (rng.standard_normal(1000) * 0.7).astype(np.float32)                # peak > 1
+    short = (rng.standard_normal(300) * 0.2).astype(np.float32)
+    c = O.prepare_clip(long, 400, "center", "wrap", peak_normalize=False).numpy()
+    assert np.array_equal(c, long[300:700])                                     # CenterCrop: start = (1000-400)//2
+    c = O.prepare_clip(long, 400, 123, "wrap", peak_normalize=False).numpy()
+    assert np.array_equal(c, long[123:523])                                     # RandomCrop at a given offset
+    w = O.prepare_clip(short, 1000, "center", "wrap", peak_normalize=False).numpy()
+    assert np.array_equal(w, np.pad(short, (350, 350), "wrap"))                 # PadToSize('wrap'): offset = padding // 2
+    zc = O.prepare_clip(short, 1000, 0, "zero", peak_normalize=False).numpy()
+    assert np.array_equal(zc[:300], short) and not zc[300:].any()               # collate: zeros after the clip
+    n = O.prepare_clip(long, 1000, "center", "wrap", peak_normalize=True)
+    assert float(n.abs().max()) == 1.0 and torch.equal(n, torch.from_numpy(long) / torch.from_numpy(long).abs().max())
+    q = O.prepare_clip(short, 300, "center", "wrap", peak_normalize=True)
+    assert torch.equal(q, torch.from_numpy(short))                              # not too loud: untouched
+
+
+def test_device_agnostic_restatement_is_the_f32_oracle_on_cpu():
+    """forward_on_device (what bench.py runs on the GPU as the torch-op baseline) is the same op sequence as
+    forward_f32: bit-identical on CPU tensors."""
+    import torch
+    from oracle import leaf_oracle as O
+    from tests.util import load_golden
+    case, x, prm, z = load_golden("cfg1_default")
+    a = O.forward_f32(x, prm, case.K, case.H)
+    b = O.forward_on_device(x, prm, case.K, case.H)
+    assert torch.equal(a, b)
