@@ -89,15 +89,24 @@ typedef struct leafk_grads {
  * reference's data pipeline does on the CPU before Leaf.forward -- PadToSize('wrap') / CenterCrop / RandomCrop
  * (utilities/data/raw_transforms.py:121-160), the collate function's zero padding (utilities/data/utils.py:8-28) and
  * PeakNormalization(only_too_loud_sounds) (raw_transforms.py:334-344).  Sample i (0 <= i < T) of prepared clip b is
- * raw[b*ld + (i + start[b])] when 0 <= i + start[b] < length[b]; outside that range the index wraps around modulo
- * length[b] (wrap != 0) or the sample is zero; the value is divided by divisor[b].  Any pointer may be NULL
- * (start 0, length T, divisor 1).  All arrays are DEVICE pointers of B entries. */
+ * raw[b*ld + (i + start[b])] when 0 <= i + start[b] < length[b]; outside that range it is, by pad_mode,
+ *   LEAFK_PAD_ZERO   0 (the collate function's zero padding)
+ *   LEAFK_PAD_WRAP   the index taken modulo length[b]                        (np.pad 'wrap': PadToSize_NP, raw_transforms.py:143-160)
+ *   LEAFK_PAD_EDGE   the first / last sample of the clip                      (F.pad 'replicate': what PadToSize(mode='wrap') does, :162-183)
+ *   LEAFK_PAD_VALUE  pad_value[b], e.g. the clip's minimum                   (PadToSize(mode='constant') pads with signal.min(), :172)
+ * and the value is divided by divisor[b].  Any pointer may be NULL (start 0, length T, divisor 1, pad value 0).
+ * All arrays are DEVICE pointers of B entries. */
+#define LEAFK_PAD_ZERO 0
+#define LEAFK_PAD_WRAP 1
+#define LEAFK_PAD_EDGE 2
+#define LEAFK_PAD_VALUE 3
 typedef struct leafk_clip_prep {
   const int* start;
   const int* length;
   const float* divisor;
   long long ld;   /* row stride of the raw waveform buffer in samples; 0 = T */
-  int wrap;
+  int pad_mode;
+  const float* pad_value;
 } leafk_clip_prep;
 
 /* Static configuration: what Leaf.__init__ derives (frontend.py:38-39, 65-73, 84). */
@@ -136,6 +145,9 @@ size_t leafk_workspace_bytes(const leafk_config* cfg, int B, int n_frames);
  * (only_too_loud == 0), else 1.  One pass over the waveform; use the result as leafk_clip_prep.divisor. */
 int leafk_peak_divisors(const leafk_config* cfg, const float* x, int B, int T, int only_too_loud,
                         float* divisor_out, void* stream);
+/* minimum_out[b] = smallest raw sample of clip b over [0, length[b]) (cfg->prep gives start / length / ld; the pad value
+ * of PadToSize(mode='constant')). */
+int leafk_clip_minimum(const leafk_config* cfg, const float* x, int B, int T, float* minimum_out, void* stream);
 
 /* Whole-clip forward: replaces Leaf.forward (frontend.py:78-89).
  *   x    (B,1,T) contiguous fp32                      -> out (B,F,N) contiguous fp32

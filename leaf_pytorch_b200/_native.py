@@ -25,7 +25,7 @@ SYMBOLS = (
     "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end", "leafk_profile_k1_clock", "leafk_profile_tc_schedule",
     "leafk_forward_host_async", "leafk_event_create", "leafk_event_destroy", "leafk_event_synchronize",
     "leafk_train_supported", "leafk_train_workspace_bytes", "leafk_forward_train", "leafk_backward_saved",
-    "leafk_backward_saved_workspace_bytes", "leafk_async_status", "leafk_status_message", "leafk_peak_divisors",
+    "leafk_backward_saved_workspace_bytes", "leafk_async_status", "leafk_status_message", "leafk_peak_divisors", "leafk_clip_minimum",
     "leafk_preemp_forward", "leafk_preemp_backward", "leafk_preemp_backward_workspace_bytes", "leafk_instnorm_forward",
     "leafk_instnorm_backward",
 )
@@ -46,7 +46,10 @@ class Grads(C.Structure):
 class ClipPrep(C.Structure):
     """leafk_clip_prep: per-clip crop start / raw length / peak divisor applied while the kernels stage the waveform."""
     _fields_ = [("start", C.c_void_p), ("length", C.c_void_p), ("divisor", C.c_void_p), ("ld", C.c_longlong),
-                ("wrap", C.c_int)]
+                ("pad_mode", C.c_int), ("pad_value", C.c_void_p)]
+
+
+PAD_MODES = {"zero": 0, "wrap": 1, "edge": 2, "min": 3}
 
 
 class Config(C.Structure):
@@ -125,6 +128,8 @@ def lib() -> C.CDLL:
         L.leafk_backward_saved.restype = i
         L.leafk_backward_saved.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, vp, C.POINTER(Grads),
                                            vp, vp, sz, vp]
+        L.leafk_clip_minimum.restype = i
+        L.leafk_clip_minimum.argtypes = [C.POINTER(Config), vp, i, i, vp, vp]
         L.leafk_peak_divisors.restype = i
         L.leafk_peak_divisors.argtypes = [C.POINTER(Config), vp, i, i, i, vp, vp]
         L.leafk_preemp_forward.restype = i

@@ -40,14 +40,15 @@ struct Geom {
   const int* clip_start;
   const int* clip_len;
   const float* clip_div;
-  int clip_wrap;
+  const float* clip_padval;
+  int clip_pad;            // LEAFK_PAD_*: 0 zero, 1 wrap, 2 edge (replicate), 3 per-clip value
 };
 
 // What a kernel needs to read clip b: row offset, crop start, raw length, divisor.
 struct ClipView {
   size_t row;
   int start, len;          // clip lengths are below 2^30 (checked on the host), crop offsets within +-2^29
-  float div;
+  float div, padval;
   bool prep;
 };
 
@@ -65,6 +66,7 @@ __device__ __forceinline__ ClipView clip_view(const Geom& g, int b) {
   v.start = g.clip_start ? g.clip_start[b] : 0;
   v.len = g.clip_len ? g.clip_len[b] : (int)g.T_total;
   v.div = g.clip_div ? g.clip_div[b] : 1.0f;
+  v.padval = g.clip_padval ? g.clip_padval[b] : 0.0f;
   return v;
 }
 // sample wi of the window (= sample t_off + wi of the prepared clip); the caller has checked 0 <= wi < T_win and that
@@ -73,9 +75,14 @@ __device__ __forceinline__ float clip_sample(const Geom& g, const float* x, cons
   if (!v.prep) return load_sample(x, v.row, wi, g.x_fmt);
   int j = (int)(g.t_off + wi) + v.start;
   if (j < 0 || j >= v.len) {
-    if (!g.clip_wrap || v.len <= 0) return 0.f;
-    j %= v.len;
-    if (j < 0) j += v.len;
+    if (g.clip_pad == 3) return v.padval / v.div;
+    if (g.clip_pad == 0 || v.len <= 0) return 0.f;
+    if (g.clip_pad == 2) {
+      j = j < 0 ? 0 : v.len - 1;
+    } else {
+      j %= v.len;
+      if (j < 0) j += v.len;
+    }
   }
   return load_sample(x, v.row, j, g.x_fmt) / v.div;
 }

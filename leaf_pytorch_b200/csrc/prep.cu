@@ -47,16 +47,50 @@ peak_divisor_kernel(const Geom g, const float* __restrict__ x, int only_too_loud
   }
 }
 
+// one block per clip: smallest raw sample over [0, length)
+__global__ void __launch_bounds__(256)
+clip_minimum_kernel(const Geom g, const float* __restrict__ x, float* __restrict__ min_out) {
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const ClipView cv = clip_view(g, b);
+  float mn = 3.0e38f;
+  for (int i = tid; i < cv.len; i += blockDim.x) mn = fminf(mn, load_sample(x, cv.row, i, g.x_fmt));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  if (lane == 0) red[warp] = mn;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) mn = fminf(mn, red[w]);
+    min_out[b] = cv.len > 0 ? mn : 0.f;
+  }
+}
+
 void geom_apply_prep(const leafk_config* cfg, Geom* g) {
   const leafk_clip_prep* p = cfg->prep;
   if (p == nullptr) return;
-  g->clip_start = p->start; g->clip_len = p->length; g->clip_div = p->divisor; g->clip_wrap = p->wrap ? 1 : 0;
+  g->clip_start = p->start; g->clip_len = p->length; g->clip_div = p->divisor;
+  g->clip_padval = p->pad_value; g->clip_pad = p->pad_mode;
   if (p->ld > 0) g->ldx = p->ld;
 }
 
 }  // namespace leafk
 
 using namespace leafk;
+
+extern "C" int leafk_clip_minimum(const leafk_config* cfg, const float* x, int B, int T, float* minimum_out, void* stream) {
+  if (!cfg || !x || !minimum_out) return fail(LEAFK_EINVAL, "null pointer argument");
+  if (B < 1 || T < 1) return fail(LEAFK_EINVAL, "bad B/T (%d,%d)", B, T);
+  Geom g;
+  memset(&g, 0, sizeof(g));
+  g.B = B; g.T_total = T; g.T_win = T; g.t_off = 0; g.ldx = T;
+  g.x_fmt = cfg->input_format == LEAFK_INPUT_S16 ? 1 : 0;
+  geom_apply_prep(cfg, &g);
+  clip_minimum_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(g, x, minimum_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(LEAFK_ECUDA, "clip_minimum launch: %s", cudaGetErrorString(e));
+  count_launch(1);
+  return LEAFK_OK;
+}
 
 extern "C" int leafk_peak_divisors(const leafk_config* cfg, const float* x, int B, int T, int only_too_loud,
                                    float* divisor_out, void* stream) {

@@ -228,9 +228,9 @@ class Leaf(nn.Module):
         return out.unsqueeze(1) if self.out_layout == "b1fn" else out
 
     def forward_prepared(self, x_raw: torch.Tensor, n_samples: int, raw_lengths=None, starts="center",
-                         pad_mode: str = "wrap", peak_normalize: bool = True) -> torch.Tensor:
+                         pad_mode: str = "edge", peak_normalize: bool = True) -> torch.Tensor:
         """Features of raw, unequal-length clips without a prepared copy of the batch: every clip is cropped
-        (``starts`` "center" or per-clip offsets) or padded (``pad_mode`` "wrap" / "zero") to ``n_samples`` and, when
+        (``starts`` "center" or per-clip offsets) or padded (``pad_mode`` "edge" / "min" / "wrap" / "zero") to ``n_samples`` and, when
         its peak exceeds 1, peak-normalised -- the reference's per-clip transforms (utilities/data/raw_transforms.py:
         121-160, 334-344; utilities/data/utils.py:8-28) -- inside the kernels' own staging of the waveform.
         ``x_raw`` (B,1,Traw) float32 or int16 PCM on the GPU, ``raw_lengths`` (B,) true lengths."""

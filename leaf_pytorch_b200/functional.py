@@ -55,28 +55,31 @@ class LeafSpec:
 
 class ClipPrep:
     """Per-clip preparation applied on the fly by the kernels (leafk_clip_prep): sample i of prepared clip b is
-    ``raw[b, 0, i + start[b]]`` inside ``[0, length[b])`` -- outside, the index wraps around (``wrap``) or the sample is
-    zero -- divided by ``divisor[b]``.  Built by :func:`prepare_clips`."""
+    ``raw[b, 0, i + start[b]]`` inside ``[0, length[b])`` -- outside, by ``pad_mode``: zero, the index wrapped around,
+    the clip's edge sample, or ``pad_value[b]`` -- divided by ``divisor[b]``.  Built by :func:`prepare_clips`."""
 
-    def __init__(self, n_samples: int, start=None, length=None, divisor=None, ld: int = 0, wrap: bool = False):
+    def __init__(self, n_samples: int, start=None, length=None, divisor=None, ld: int = 0, pad_mode: str = "zero",
+                 pad_value=None):
         self.n_samples = int(n_samples)
-        self.start, self.length, self.divisor = start, length, divisor
-        self.struct = N.ClipPrep(None if start is None else start.data_ptr(), None if length is None else length.data_ptr(),
-                                 None if divisor is None else divisor.data_ptr(), int(ld), int(bool(wrap)))
+        self.start, self.length, self.divisor, self.pad_value = start, length, divisor, pad_value
+        p = lambda t: None if t is None else t.data_ptr()
+        self.struct = N.ClipPrep(p(start), p(length), p(divisor), int(ld), N.PAD_MODES[pad_mode], p(pad_value))
 
 
 def prepare_clips(spec: "LeafSpec", x_raw: torch.Tensor, n_samples: int, raw_lengths=None, starts="center",
                   pad_mode: str = "wrap", peak_normalize: bool = True, only_too_loud: bool = True) -> ClipPrep:
     """GPU side of the reference's per-clip input transforms: crop every raw clip to ``n_samples`` (``starts``:
     "center" = CenterCrop, or an int tensor of crop offsets = RandomCrop drawn by the caller), pad shorter clips
-    (``pad_mode`` "wrap" = PadToSize('wrap'), "zero" = the collate function's zero padding) and, optionally, peak-
-    normalise clips whose peak exceeds 1 (PeakNormalization(only_too_loud_sounds)).  ``x_raw`` (B,1,Traw) float32 or
+    (``pad_mode``: "edge" = what the reference's PadToSize(mode='wrap') does -- F.pad 'replicate' --, "min" = its
+    PadToSize(mode='constant'), which pads with the clip's minimum, "wrap" = np.pad 'wrap' (PadToSize_NP), "zero" = the
+    collate function's zero padding) and, optionally, peak-normalise clips whose peak exceeds 1
+    (PeakNormalization(only_too_loud_sounds)).  ``x_raw`` (B,1,Traw) float32 or
     int16 on the GPU holds the raw clips row by row, ``raw_lengths`` (B,) their true lengths (default Traw).  Nothing is
     copied: the result only describes the view; one small kernel computes the peak divisors."""
     if not x_raw.is_cuda or x_raw.dim() != 3 or x_raw.shape[1] != 1 or not x_raw.is_contiguous():
         raise ValueError("x_raw must be a contiguous CUDA tensor of shape (B,1,Traw)")
-    if pad_mode not in ("wrap", "zero"):
-        raise ValueError("pad_mode must be 'wrap' or 'zero'")
+    if pad_mode not in N.PAD_MODES:
+        raise ValueError(f"pad_mode must be one of {sorted(N.PAD_MODES)}")
     B, _, Traw = x_raw.shape
     dev = x_raw.device
     length = torch.full((B,), Traw, dtype=torch.int32, device=dev) if raw_lengths is None else \
@@ -93,14 +96,21 @@ def prepare_clips(spec: "LeafSpec", x_raw: torch.Tensor, n_samples: int, raw_len
         start = torch.as_tensor(starts, dtype=torch.int32, device=dev).contiguous()
         if start.numel() != B:
             raise ValueError("starts must hold B crop offsets")
-    prep = ClipPrep(n_samples, start, length, None, ld=Traw, wrap=pad_mode == "wrap")
-    if peak_normalize:
-        div = torch.empty(B, dtype=torch.float32, device=dev)
-        cfg = spec.config(x_raw.dtype, prep=prep)
-        with torch.cuda.device(dev):
+    prep = ClipPrep(n_samples, start, length, None, ld=Traw, pad_mode=pad_mode)
+    padval = None
+    with torch.cuda.device(dev):
+        if pad_mode == "min":
+            padval = torch.empty(B, dtype=torch.float32, device=dev)
+            cfg = spec.config(x_raw.dtype, prep=prep)
+            N.check(N.lib().leafk_clip_minimum(C.byref(cfg), _ptr(x_raw), B, int(n_samples), _ptr(padval), _stream_ptr(dev)),
+                    "leafk_clip_minimum")
+            prep = ClipPrep(n_samples, start, length, None, ld=Traw, pad_mode=pad_mode, pad_value=padval)
+        if peak_normalize:
+            div = torch.empty(B, dtype=torch.float32, device=dev)
+            cfg = spec.config(x_raw.dtype, prep=prep)
             N.check(N.lib().leafk_peak_divisors(C.byref(cfg), _ptr(x_raw), B, int(n_samples), int(only_too_loud), _ptr(div),
                                                 _stream_ptr(dev)), "leafk_peak_divisors")
-        prep = ClipPrep(n_samples, start, length, div, ld=Traw, wrap=pad_mode == "wrap")
+            prep = ClipPrep(n_samples, start, length, div, ld=Traw, pad_mode=pad_mode, pad_value=padval)
     return prep
 
 

@@ -19,7 +19,7 @@ def oracle_prm(fe):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.int16])
-@pytest.mark.parametrize("pad_mode", ["wrap", "zero"])
+@pytest.mark.parametrize("pad_mode", ["edge", "min", "wrap", "zero"])
 def test_prepared_forward_equals_cpu_transforms_then_forward(dtype, pad_mode):
     """Raw clips of unequal length, some too loud: forward_prepared (crop / pad / peak-normalise inside the kernels'
     staging) == the reference's CPU transforms followed by the plain forward."""
@@ -45,6 +45,29 @@ def test_prepared_forward_equals_cpu_transforms_then_forward(dtype, pad_mode):
         assert torch.equal(got, same), (algo, (got - same).abs().max().item())           # same arithmetic, no copy of the batch
         ref = O.forward_f32(prepared, oracle_prm(fe), 401, 160).numpy()
         assert_close(got.cpu().numpy(), ref, f"prepared clips {dtype} {pad_mode} {algo}")
+
+
+@pytest.mark.parametrize("which", ["prep_eval", "prep_train"])
+def test_prepared_forward_matches_reference_transforms_golden(which):
+    """Golden vectors made with the reference's own PadToSize / CenterCrop / RandomCrop classes and the reference Leaf
+    (tests/golden/make_golden_prep.py): the kernels' on-the-fly preparation gives the same features."""
+    import os
+    import leaf_pytorch_b200 as L
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", which + ".npz"))
+    n, lens = int(z["n_samples"]), torch.from_numpy(z["lengths"])
+    raw = torch.from_numpy(z["raw"]).unsqueeze(1).cuda()
+    for algo in ("auto", "fp32"):
+        fe = L.Leaf(algo=algo).cuda()
+        with torch.no_grad():
+            if which == "prep_eval":      # PadToSize(size, 'wrap') [= replicate], CenterCrop, PeakNormalization
+                got = fe.forward_prepared(raw, n, raw_lengths=lens, starts="center", pad_mode="edge")
+            else:                         # PadToSize(size, 'constant') [= clip minimum], RandomCrop offsets, PeakNormalization
+                pad_front = (n - lens).clamp(min=0) // 2
+                starts = torch.where(lens < n, -pad_front, torch.from_numpy(z["starts"])).to(torch.int32)
+                got = fe.forward_prepared(raw, n, raw_lengths=lens, starts=starts.cuda(), pad_mode="min")
+            same = fe(torch.from_numpy(z["prepared"]).cuda())
+        assert torch.equal(got, same), (which, algo)
+        assert_close(got.cpu().numpy(), z["out"], f"{which} {algo}")
 
 
 def test_random_crop_offsets_and_training_through_prepared_clips():

@@ -152,3 +152,29 @@ def test_device_agnostic_restatement_is_the_f32_oracle_on_cpu():
     a = O.forward_f32(x, prm, case.K, case.H)
     b = O.forward_on_device(x, prm, case.K, case.H)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("which", ["prep_eval", "prep_train"])
+def test_prepare_clip_against_the_reference_transform_classes(which):
+    """tests/golden/prep_*.npz were made by tests/golden/make_golden_prep.py with the reference's own PadToSize /
+    CenterCrop / RandomCrop classes (cut out of raw_transforms.py) and the reference Leaf: the oracle's restatement of
+    the transforms reproduces the prepared clips bit for bit, and its forward the features."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import leaf_oracle as O
+    import leaf_pytorch_b200 as L
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", which + ".npz"))
+    n = int(z["n_samples"])
+    clips = []
+    for i, ln in enumerate(z["lengths"]):
+        raw = z["raw"][i, :ln]
+        if which == "prep_eval":
+            clips.append(O.prepare_clip(raw, n, "center", "edge"))
+        else:
+            clips.append(O.prepare_clip(raw, n, "center" if ln < n else int(z["starts"][i]), "min"))
+    got = torch.stack(clips).unsqueeze(1)
+    assert torch.equal(got, torch.from_numpy(z["prepared"]))
+    fe = L.Leaf()
+    prm = O.params_from_state_dict({k: v.detach() for k, v in fe.state_dict().items()})
+    assert torch.equal(O.forward_f32(got, prm, 401, 160), torch.from_numpy(z["out"]))
