@@ -263,7 +263,7 @@ def run_reference(args, rank: int, world: int, emit):
 
 def k1_source_sha16() -> str:
     h = hashlib.sha256()
-    for name in ("k1_tc.cu", "k1_tc_layout.cuh", "tc_ptx.cuh", "k0_banks.cu"):
+    for name in ("k1_tc_kernel.cuh", "k1_tc.cu", "k1_tc_layout.cuh", "tc_ptx.cuh", "k0_banks.cu"):
         with open(os.path.join(ROOT, "leaf_pytorch_b200", "csrc", name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]

@@ -7,7 +7,7 @@
 // Tensor-core path (geometries the training kernel covers, k1_tc_train_filters_per_group() > 0):
 //   leafk_forward_train   T0 k0_banks_train_kernel   banks h, tau*h, (tau^2/sigma^3 - 1/sigma)*h      (k0_banks.cu)
 //                         T1 k1_tc_kernel<.,.,1,.>   y, z, v correlations; pools e and the three bilinear forms
-//                                                    Q_mu, Q_sigma, Q_poolw with the pooling windows     (k1_tc.cu)
+//                                                    Q_mu, Q_sigma, Q_poolw with the pooling windows     (k1_tc_kernel.cuh)
 //                         T2 k2_pcen_kernel          p -> floor -> PCEN -> out; assembles p and the Q's  (k2_pcen.cu)
 //   leafk_backward_saved  B1 bwd_pcen_kernel         per (clip, filter) row: PCEN + smoother backward (forward scan to
 //                                                    rebuild M, reverse affine scan for the smoother adjoint), floor

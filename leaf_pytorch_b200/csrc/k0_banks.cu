@@ -13,7 +13,7 @@
 //   cprm[f][8]      constrained / derived per-filter constants (see CP_* in leafk_common.cuh)
 //   w32[k][c]       fp32 bank, tap-major, channels padded to C2p, taps padded to Kp with zeros
 //   g32[k][f]       fp32 Gaussian pooling windows, tap-major
-//   w16             fp16 hi/lo bank in the tcgen05 shared-memory layout (see k1_tc.cu), optional
+//   w16             fp16 hi/lo bank in the tcgen05 shared-memory layout (see k1_tc_kernel.cuh), optional
 #include "leafk_common.cuh"
 #include "k1_tc_layout.cuh"
 #include <cuda_fp16.h>

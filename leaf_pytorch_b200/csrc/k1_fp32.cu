@@ -6,7 +6,7 @@
 // without ever materialising the (B,2F,T) activation the reference writes to memory.
 //
 // This is the general-geometry path (any F, K, H) and the arithmetic reference for the tensor-core
-// kernel in k1_tc.cu; it is bound by FP32-FMA issue, not HBM (~12.9 kFLOP per byte).
+// kernel in k1_tc_kernel.cuh; it is bound by FP32-FMA issue, not HBM (~12.9 kFLOP per byte).
 //
 // One CTA = one (clip, tile of TL=512 e-samples).  The clip window (TL + Kp samples) sits in
 // shared memory; the bank is streamed through shared memory in slices of 16 taps (cp.async, double

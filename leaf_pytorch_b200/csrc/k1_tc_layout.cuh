@@ -1,6 +1,6 @@
 // Shared-memory operand layouts and the shared-memory budget of the tensor-core (tcgen05) Gabor
 // kernel.  Used by the bank prologue (k0 writes the B operand into global memory already in this
-// layout), by k1_tc.cu (which copies it into shared memory unchanged) and by the host planner.
+// layout), by k1_tc_kernel.cuh (which copies it into shared memory unchanged) and by the host planner.
 //
 // B operand = Gabor bank of one channel group, fp16, "N x K, K-major, no swizzle" canonical
 // layout: 8x8 core matrices of 128 contiguous bytes (8 rows x 16 B).  The kernel runs on CTA PAIRS

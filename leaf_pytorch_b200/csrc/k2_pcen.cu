@@ -198,7 +198,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
 }
 
 // Training forward: Q[kind-1][b][f][n] = sum over the tiles overlapping frame n of the partial sums of pooled quantity
-// `kind` (1..3: Q_mu, Q_sigma, Q_poolw; k1_tc.cu), in tile order.  One thread per output element, frames fastest:
+// `kind` (1..3: Q_mu, Q_sigma, Q_poolw; k1_tc_kernel.cuh), in tile order.  One thread per output element, frames fastest:
 // nothing but index arithmetic and <= ceil(K/TL)+1 loads, so the kernel lives on memory-level parallelism (full
 // occupancy) -- as rows of the PCEN kernel (one warp per 100 frames, 59 registers) it took 0.44 ms at 1024 x 80 x 100.
 __global__ void __launch_bounds__(256)
