@@ -159,12 +159,12 @@ k1_fp32_kernel(const Geom g, const float* __restrict__ x, const float* __restric
   }
   __syncthreads();
   // ---- fixed-order sum over chunks -> partial pooled sums of this tile -----------------------
-  float* dst = ppart + ((size_t)b * g.n_tiles + tile) * g.SL * g.F;
-  for (int i = tid; i < g.SL * g.F; i += blockDim.x) {       // i = f*SL + slot: (filter, slot) layout, slot fastest
+  float* dst = ppart + ((size_t)b * g.F * g.n_tiles + tile) * g.SL;      // layout [clip][filter][tile][slot]
+  for (int i = tid; i < g.SL * g.F; i += blockDim.x) {       // i = f*SL + slot
     const int f = i / g.SL, slot = i % g.SL;
     float s = 0.f;
     for (int ch = 0; ch < F32_NCH; ++ch) s += pitem[(ch * g.SL + slot) * g.F + f];
-    dst[i] = s;
+    dst[(size_t)f * g.n_tiles * g.SL + slot] = s;
   }
 }
 

@@ -48,7 +48,7 @@ static int sm_count(cudaError_t* err) {
 }
 
 // Training forward: FB filters per group (16 -> CG 96, 8 -> CG 48); partial sums of the 4 pooled quantities go to
-// ppart[b][tile][kind*F + f][slot].
+// ppart[b][kind*F + f][tile][slot].
 cudaError_t launch_k1_tc_train(const Geom& g, const float* x, const uint8_t* w16t, int FB, int n_groups,
                                const float* tprm, float* ppart, int* done, cudaStream_t stream) {
   cudaError_t err;

@@ -615,7 +615,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         const int fl = idx / g.SL, slot = idx - fl * g.SL;
         const int f = __ldg(gperm + fl);                      // sorted position -> filter
         int4 o = make_int4(((fl / NV) * 4 * g.SL + slot) * NV + fl % NV, -1, 0, 0);
-        if (f < g.F) { o.y = f * g.SL + slot; o.z = 2 * (int)__ldg(cprm + (size_t)f * 8 + CP_WSCALE); }
+        if (f < g.F) { o.y = f * g.n_tiles * g.SL + slot; o.z = 2 * (int)__ldg(cprm + (size_t)f * 8 + CP_WSCALE); }
         s_out[idx] = o;
       }
     } else {
@@ -632,7 +632,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
         if (f < g.F) {
           const float* tp = ta.tprm + (size_t)f * 8;
           const int shy = (int)__ldg(tp + 1), shz = (int)__ldg(tp + 2), shv = (int)__ldg(tp + 3);
-          o.y = (kind * g.F + f) * g.SL + slot;
+          o.y = (kind * g.F + f) * g.n_tiles * g.SL + slot;
           o.z = shy + (kind == 1 ? shz : (kind == 2 ? shv : shy));
         }
         s_out[idx] = o;
@@ -746,7 +746,7 @@ k1_tc_kernel(const Geom g, const float* __restrict__ x, const uint8_t* __restric
       tile_end_rowsums<NV, NSLOT>(acc, pw_buf + (size_t)e * g.SL * NV, red, lane, nb, n_first, n_last, g.SL);
       named_bar_sync(BAR_EPI, EPI_WARPS * 32);
       const int sx = misc->sx_ring[it & 3];
-      float* dst = ppart + ((size_t)b * g.n_tiles + tile) * g.SL * FV;
+      float* dst = ppart + ((size_t)b * FV * g.n_tiles + tile) * g.SL;     // layout [clip][virtual filter][tile][slot]
       tile_end_store(pw_buf, s_out, g.SL * 2 * NV, etid, valid, dst, sx, g.SL * NV);
       sig_b = (valid && tm.done != nullptr) ? b : -1;   // published off the critical path (phase 1 of the next tile)
     }

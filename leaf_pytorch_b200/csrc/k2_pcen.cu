@@ -9,7 +9,7 @@
 // a register between steps (and in/out of the kernel for chunked long-form audio).
 //
 // One warp = one (clip, filter) row; lane = frame within a group of 32 consecutive frames, so the
-// partial sums (layout [clip][tile][filter][slot], slot fastest) are read and `out` is written with
+// partial sums (layout [clip][filter][tile][slot]: the partials of a row are contiguous) are read and `out` is written with
 // unit stride across lanes.  Grid-stride over rows, no shared memory, no block barrier.  This is the
 // only HBM-bound stage of the path (~14 B per output element).
 #include "leafk_common.cuh"
@@ -46,7 +46,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
   const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;       // clip length <= 2^30 (checked on the host)
   const int n_end = g.n_begin + g.n_count;
   const int FV = a.q_out != nullptr ? 4 * g.F : g.F;            // virtual filters per (clip, tile) block
-  const size_t tile_stride = (size_t)FV * g.SL;
+  const size_t tile_stride = (size_t)g.SL;                      // layout [clip][virtual filter][tile][slot]: a row's partials are contiguous
 
   for (int row = ROWBLOCK ? blockIdx.x : blockIdx.x * K2_WARPS + warp; row < rows;
        row += ROWBLOCK ? gridDim.x : gridDim.x * K2_WARPS) {
@@ -72,7 +72,7 @@ k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, 
       }
       __syncwarp();
     }
-    const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + (size_t)f * g.SL;
+    const float* pbase = ppart + ((size_t)b * FV + f) * g.n_tiles * g.SL;
     const size_t ooff = (size_t)b * a.ldo_b + (size_t)f * a.ldo_f;
     float* orow = a.out + ooff;
     __nv_bfloat16* orow16 = reinterpret_cast<__nv_bfloat16*>(a.out) + ooff;
@@ -206,7 +206,7 @@ q_assemble_kernel(const Geom g, const float* __restrict__ ppart, float* __restri
                   unsigned long long hop_magic) {
   const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;
   const long long per_kind = (long long)g.B * g.F * g.n_count, total = 3 * per_kind;
-  const size_t tile_stride = (size_t)4 * g.F * g.SL;
+  const size_t tile_stride = (size_t)g.SL;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int kind = (int)(idx / per_kind) + 1;
     const long long r = idx - (long long)(kind - 1) * per_kind;
@@ -218,7 +218,7 @@ q_assemble_kernel(const Geom g, const float* __restrict__ ppart, float* __restri
     if (wlo < te_lo) wlo = te_lo;
     if (whi > te_hi - 1) whi = te_hi - 1;
     const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
-    const float* pbase = ppart + (size_t)b * g.n_tiles * tile_stride + ((size_t)kind * g.F + f) * g.SL;
+    const float* pbase = ppart + ((size_t)b * 4 * g.F + (size_t)kind * g.F + f) * g.n_tiles * g.SL;
     float s = 0.f;
     for (int i = i0; i <= i1; ++i) {
       const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;

@@ -123,7 +123,7 @@ struct Workspace {
   size_t off_g32;    // float[K*F]   Gaussian pooling windows, tap-major ([k][f])
   size_t off_w16;    // uint8[...]   fp16 hi/lo bank in UMMA smem layout (tensor-core path)
   size_t off_tcmap;  // int[Fp] sorted position -> filter, then int[groups][16] zone table (k1_tc_layout.cuh)
-  size_t off_ppart;  // float[B][n_tiles][F][SL] partial pooled sums (slot fastest)
+  size_t off_ppart;  // float[B][F][n_tiles][SL] partial pooled sums (slot fastest; a (clip, filter) row's partials contiguous)
   size_t off_flags;  // int[64]      slice-ready flags of the host-pipelined forward
   size_t off_done;   // int[B]       per clip: epilogue warps of K1 that have stored a tile of it (K2 starts a clip at
                      //              n_tiles * n_groups * 8, see k2_pcen.cu)
