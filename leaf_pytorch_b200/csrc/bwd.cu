@@ -73,6 +73,10 @@ bwd_pcen_kernel(int B, int F, int N, const PcenBwdArgs a) {
 
   float s_delta = 0.f, s_alpha = 0.f, s_root = 0.f, s_w = 0.f, s_bias = 0.f, s_mu = 0.f, s_sg = 0.f, s_pw = 0.f;
   float w = 0.f, om = 1.f;
+  // rows of <= 128 frames (1 s clips) keep the adjoint seeds in registers between the two sweeps; longer rows park
+  // them in the scratch buffer
+  const bool in_regs = nseg == 1;
+  float k_t1[4] = {0.f, 0.f, 0.f, 0.f}, k_dM[4] = {0.f, 0.f, 0.f, 0.f}, k_pm[4] = {0.f, 0.f, 0.f, 0.f};
 
   if (a.compression) {
     w = clamp_nan(a.ema_w[f], 0.f, 1.f);
@@ -126,10 +130,13 @@ bwd_pcen_kernel(int B, int F, int N, const PcenBwdArgs a) {
           s_delta += G - go[j] * q * dq1;
           s_alpha -= G * p[j] * Dma * (l2D * 0.69314718056f);
           s_root -= go[j] * (u * uq1 * (l2u * 0.69314718056f) - dq * ldelta) * (q * q);
-          float* sc = a.scratch + (row + seg0 + nl) * 3;
-          sc[0] = G * Dma;
-          sc[1] = -G * alpha * p[j] * Dma / D;
-          sc[2] = p[j] - prev;
+          const float v_t1 = G * Dma, v_dM = -G * alpha * p[j] * Dma / D, v_pm = p[j] - prev;
+          if (in_regs) {
+            k_t1[j] = v_t1; k_dM[j] = v_dM; k_pm[j] = v_pm;
+          } else {
+            float* sc = a.scratch + (row + seg0 + nl) * 3;
+            sc[0] = v_t1; sc[1] = v_dM; sc[2] = v_pm;
+          }
         }
       }
       const float Al = __shfl_sync(0xffffffffu, A, 31), Cl = __shfl_sync(0xffffffffu, C, 31);
@@ -148,8 +155,12 @@ bwd_pcen_kernel(int B, int F, int N, const PcenBwdArgs a) {
       for (int j = 0; j < 4; ++j) {
         const int nl = lane * 4 + j;
         const bool ok = nl < seg_n;
-        const float* sc = a.scratch + (row + seg0 + (ok ? nl : 0)) * 3;
-        t1[j] = ok ? sc[0] : 0.f; dM[j] = ok ? sc[1] : 0.f; pm[j] = ok ? sc[2] : 0.f;
+        if (in_regs) {
+          t1[j] = k_t1[j]; dM[j] = k_dM[j]; pm[j] = k_pm[j];      // zero beyond the row's last frame
+        } else {
+          const float* sc = a.scratch + (row + seg0 + (ok ? nl : 0)) * 3;
+          t1[j] = ok ? sc[0] : 0.f; dM[j] = ok ? sc[1] : 0.f; pm[j] = ok ? sc[2] : 0.f;
+        }
         cnt += ok;
       }
       // composite of this lane's frames, applied from the last frame backwards:  L -> om*L + dM_j

@@ -205,28 +205,55 @@ __global__ void __launch_bounds__(256)
 q_assemble_kernel(const Geom g, const float* __restrict__ ppart, float* __restrict__ q_out, int tl_shift,
                   unsigned long long hop_magic) {
   const int te_lo = (int)g.te_lo, te_hi = (int)g.te_hi;
-  const long long per_kind = (long long)g.B * g.F * g.n_count, total = 3 * per_kind;
-  const size_t tile_stride = (size_t)g.SL;
+  const int n4 = (g.n_count + 3) / 4;                         // groups of 4 consecutive frames per thread
+  const long long rows = 3LL * g.B * g.F, total = rows * n4;
+  const size_t per_kind = (size_t)g.B * g.F;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int kind = (int)(idx / per_kind) + 1;
-    const long long r = idx - (long long)(kind - 1) * per_kind;
-    const int nrel = (int)(r % g.n_count);
-    const long long bf = r / g.n_count;
+    const long long row = idx / n4;                            // (kind-1, b, f)
+    const int q4 = (int)(idx - row * n4);
+    const int kind = (int)(row / per_kind) + 1;
+    const long long bf = row - (long long)(kind - 1) * per_kind;
     const int b = (int)(bf / g.F), f = (int)(bf - (long long)b * g.F);
-    const int n = g.n_begin + nrel;
-    int wlo = n * g.H - g.padL, whi = wlo + g.K - 1;
-    if (wlo < te_lo) wlo = te_lo;
-    if (whi > te_hi - 1) whi = te_hi - 1;
-    const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
     const float* pbase = ppart + ((size_t)b * 4 * g.F + (size_t)kind * g.F + f) * g.n_tiles * g.SL;
-    float s = 0.f;
-    for (int i = i0; i <= i1; ++i) {
-      const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
-      int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
-      if (nf < g.n_begin) nf = g.n_begin;
-      s += __ldg(pbase + (size_t)i * tile_stride + (n - nf));
+    float v[4][2];
+    int extra_lo[4], extra_hi[4];                              // tiles beyond the first two of a frame (long windows only)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                              // all loads of the 4 frames are issued before any is used
+      const int n = g.n_begin + 4 * q4 + u;
+      v[u][0] = v[u][1] = 0.f;
+      extra_lo[u] = 1; extra_hi[u] = 0;
+      if (n < g.n_begin + g.n_count) {
+        int wlo = n * g.H - g.padL, whi = wlo + g.K - 1;
+        if (wlo < te_lo) wlo = te_lo;
+        if (whi > te_hi - 1) whi = te_hi - 1;
+        const int i0 = (wlo - te_lo) >> tl_shift, i1 = (whi - te_lo) >> tl_shift;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int i = i0 + k;
+          if (i <= i1) {
+            const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
+            int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
+            if (nf < g.n_begin) nf = g.n_begin;
+            v[u][k] = __ldg(pbase + (size_t)i * g.SL + (n - nf));
+          }
+        }
+        extra_lo[u] = i0 + 2; extra_hi[u] = i1;
+      }
     }
-    q_out[idx] = s;
+    float* qrow = q_out + (size_t)row * g.n_count + 4 * q4;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = g.n_begin + 4 * q4 + u;
+      if (n >= g.n_begin + g.n_count) break;
+      float sum = v[u][0] + v[u][1];                          // tile order
+      for (int i = extra_lo[u]; i <= extra_hi[u]; ++i) {
+        const int num = te_lo + (i << tl_shift) + g.padL - g.K + 1;
+        int nf = num <= 0 ? 0 : (int)div_magic((unsigned)(num + g.H - 1), hop_magic);
+        if (nf < g.n_begin) nf = g.n_begin;
+        sum += __ldg(pbase + (size_t)i * g.SL + (n - nf));
+      }
+      qrow[u] = sum;
+    }
   }
 }
 
@@ -253,7 +280,7 @@ cudaError_t launch_k2(const Geom& g, const float* ppart, const PcenArgs& a, cuda
   if (err != cudaSuccess || a.q_out == nullptr) return err;
   // training forward: the three pooled bilinear forms, one thread per output element (after K2 in stream order, i.e.
   // after the whole Gabor grid)
-  const long long total = 3LL * g.B * g.F * g.n_count;
+  const long long total = 3LL * g.B * g.F * ((g.n_count + 3) / 4);    // 4 consecutive frames per thread
   long long qblocks = (total + 255) / 256;
   if (qblocks > (1LL << 22)) qblocks = 1LL << 22;
   q_assemble_kernel<<<(unsigned)qblocks, 256, 0, stream>>>(g, ppart, a.q_out, tl_shift, hop_magic);
