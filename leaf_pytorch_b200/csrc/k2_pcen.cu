@@ -32,7 +32,7 @@ __device__ __forceinline__ float pow_pos(float x, float y) { return exp2f(y * lo
 // Here warp w takes the frames [n0 + 128 w, n0 + 128 w + 128) of a 1024-frame super-step, publishes the composite
 // affine map of its segment, and picks up its carry-in by composing the maps of the warps before it (<= 7 FMAs).
 template <bool ROWBLOCK>
-__global__ void __launch_bounds__(K2_WARPS * 32)
+__global__ void __launch_bounds__(K2_WARPS * 32, 6)
 k2_pcen_kernel(const Geom g, const float* __restrict__ ppart, const PcenArgs a, int tl_shift, unsigned long long hop_magic) {
   __shared__ float s_A[K2_WARPS], s_C[K2_WARPS], s_first;
   // Programmatic dependent launch: this grid is scheduled under the tail of the kernel that writes the partial sums.
