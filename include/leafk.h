@@ -255,6 +255,12 @@ int leafk_event_synchronize(void* ev);
 
 /* 1 when LEAFK_ALGO_TC covers (F,K,H); LEAFK_ALGO_AUTO falls back to LEAFK_ALGO_FP32 otherwise. */
 int leafk_tc_supported(int F, int K, int H);
+/* Host-only description of how the tensor-core kernels would run (F,K,H): channel groups of the inference forward
+ * (0 = not covered, the FP32 kernel runs) and channels per group (a multiple of 16; above 96 = the single-group "lean"
+ * plan of F = 49..64), filters per group of the training forward (16 or 8; 0 = generic FP32 backward), and the frame
+ * slots an 8-sample row touches.  Any output pointer may be NULL. */
+int leafk_describe_plan(int F, int K, int H, int* forward_groups, int* forward_channels_per_group,
+                        int* train_filters_per_group, int* frame_slots);
 
 /* Per-kernel device timing for the roofline report: between begin and end every forward issued
  * by this thread records CUDA events around K0 (bank prologue), K1 (Gabor GEMM + pooling) and K2

@@ -25,7 +25,7 @@ SYMBOLS = (
     "leafk_backward_workspace_bytes", "leafk_forward_host", "leafk_launch_count", "leafk_tc_supported", "leafk_profile_begin", "leafk_profile_end", "leafk_profile_k1_clock", "leafk_profile_tc_schedule",
     "leafk_forward_host_async", "leafk_event_create", "leafk_event_destroy", "leafk_event_synchronize",
     "leafk_train_supported", "leafk_train_workspace_bytes", "leafk_forward_train", "leafk_backward_saved",
-    "leafk_backward_saved_workspace_bytes", "leafk_async_status", "leafk_status_message", "leafk_peak_divisors", "leafk_clip_minimum",
+    "leafk_backward_saved_workspace_bytes", "leafk_async_status", "leafk_status_message", "leafk_peak_divisors", "leafk_clip_minimum", "leafk_describe_plan",
     "leafk_preemp_forward", "leafk_preemp_backward", "leafk_preemp_backward_workspace_bytes", "leafk_instnorm_forward",
     "leafk_instnorm_backward",
 )
@@ -128,6 +128,8 @@ def lib() -> C.CDLL:
         L.leafk_backward_saved.restype = i
         L.leafk_backward_saved.argtypes = [C.POINTER(Config), C.POINTER(Params), vp, i, i, vp, vp, C.POINTER(Grads),
                                            vp, vp, sz, vp]
+        L.leafk_describe_plan.restype = i
+        L.leafk_describe_plan.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
         L.leafk_clip_minimum.restype = i
         L.leafk_clip_minimum.argtypes = [C.POINTER(Config), vp, i, i, vp, vp]
         L.leafk_peak_divisors.restype = i

@@ -543,6 +543,19 @@ int leafk_tc_supported(int F, int K, int H) {
   return k1_tc_supported(g, &why) ? 1 : 0;
 }
 
+int leafk_describe_plan(int F, int K, int H, int* forward_groups, int* forward_channels_per_group,
+                        int* train_filters_per_group, int* frame_slots) {
+  if (F < 1 || K < 2 || H < 1) return fail(LEAFK_EINVAL, "bad F/K/H (%d,%d,%d)", F, K, H);
+  const int Kp = (K + 15) / 16 * 16, SL = (TC_TILE + K - 2) / H + 1, nslot = tc::slots_per_thread(K, H);
+  int ng = 0, cg = 0;
+  const bool ok = nslot <= 5 && Kp <= 2048 && tc::channel_groups(2 * F, Kp, SL, nslot, &ng, &cg, K, H);
+  if (forward_groups) *forward_groups = ok ? ng : 0;
+  if (forward_channels_per_group) *forward_channels_per_group = ok ? cg : 0;
+  if (train_filters_per_group) *train_filters_per_group = train_supported(F, K, H) ? tc::train_filters_per_group(Kp, SL, nslot) : 0;
+  if (frame_slots) *frame_slots = nslot;
+  return LEAFK_OK;
+}
+
 void leafk_profile_begin(void) {
   g_prof_on = true;
   g_prof_n = 0;

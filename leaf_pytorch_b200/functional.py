@@ -570,6 +570,15 @@ def profile_end():
     return int(n), float(a.value), float(b.value), float(c.value)
 
 
+def describe_plan(F: int, K: int, H: int) -> dict:
+    """Host-only: how the tensor-core kernels would run this geometry (leafk_describe_plan)."""
+    a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    N.check(N.lib().leafk_describe_plan(int(F), int(K), int(H), C.byref(a), C.byref(b), C.byref(c), C.byref(d)),
+            "leafk_describe_plan")
+    return {"forward_groups": a.value, "forward_channels_per_group": b.value, "train_filters_per_group": c.value,
+            "frame_slots": d.value}
+
+
 def tc_supported(F: int, K: int, H: int) -> bool:
     """True when the tcgen05 kernel covers this geometry (else algo="auto" uses the fp32 kernel)."""
     return bool(N.lib().leafk_tc_supported(int(F), int(K), int(H)))

@@ -295,3 +295,26 @@ def test_host_side_planning_calls_work_without_a_gpu():
     assert L.leafk_train_workspace_bytes(C.byref(c), 256, 16000) > 4 * 256 * 16 * 4 * 40 * 9
     assert L.leafk_backward_saved_workspace_bytes(C.byref(c), 256, 16000, 1) > L.leafk_backward_saved_workspace_bytes(C.byref(c), 256, 16000, 0) > 0
     assert L.leafk_backward_workspace_bytes(C.byref(c), 4, 16000) > 0
+
+
+def test_kernel_plans_for_the_benchmark_and_edge_geometries():
+    """leafk_describe_plan (host only): the channel grouping / training grouping the kernels use.  F <= 48 and the
+    default window: one group; F = 49..64: one group of up to 128 channels (lean shared-memory plan) when the hop allows
+    the fast tile-end path, else two groups; F = 80: two groups of 80; training: 16 filters x 6 channels per group."""
+    import leaf_pytorch_b200.functional as LF
+    p = LF.describe_plan(40, 401, 160)
+    assert p == {"forward_groups": 1, "forward_channels_per_group": 80, "train_filters_per_group": 16, "frame_slots": 3}
+    assert LF.describe_plan(64, 401, 160)["forward_groups"] == 1 and LF.describe_plan(64, 401, 160)["forward_channels_per_group"] == 128
+    assert LF.describe_plan(56, 401, 160)["forward_channels_per_group"] == 112
+    small_hop = LF.describe_plan(64, 201, 100)                       # hop < 124: no lean plan
+    assert small_hop["forward_groups"] == 2 and small_hop["forward_channels_per_group"] == 64
+    p80 = LF.describe_plan(80, 401, 160)
+    assert (p80["forward_groups"], p80["forward_channels_per_group"]) == (2, 80)
+    assert LF.describe_plan(40, 401, 40) == {"forward_groups": 0, "forward_channels_per_group": 0, "train_filters_per_group": 0, "frame_slots": 11}
+    long_win = LF.describe_plan(8, 1601, 480)
+    assert long_win["forward_groups"] == 1 and long_win["train_filters_per_group"] == 0   # 3 banks of 1601 taps exceed shared memory: generic backward
+    many_slots = LF.describe_plan(20, 401, 100)                      # 5 frame slots: small groups, training with 8 filters per group
+    assert many_slots["frame_slots"] == 5 and many_slots["forward_channels_per_group"] <= 64 and many_slots["train_filters_per_group"] == 8
+    for F, K, H in ((40, 401, 160), (64, 401, 160), (80, 401, 160), (8, 1601, 480), (20, 401, 100), (40, 401, 40)):
+        assert LF.tc_supported(F, K, H) == (LF.describe_plan(F, K, H)["forward_groups"] > 0)
+        assert LF.train_supported(LF.LeafSpec(F=F, K=K, H=H)) == (LF.describe_plan(F, K, H)["train_filters_per_group"] > 0)
