@@ -250,7 +250,7 @@ def test_bench_reference_arm_training_config():
                           "--warmup", "1"], check=True, capture_output=True, text=True, timeout=600).stdout
     line = json.loads(out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["config"]["config_id"] == 3 and line["config"]["pass"] == "train"
-    assert line["step_clips"] == 8 and "forward+backward" in line["cpu_baseline"]["sample"] and line["value"] > 0
+    assert line["step_clips"] == 64 and "forward+backward" in line["cpu_baseline"]["sample"] and line["value"] > 0
 
 
 def test_header_constants_match_the_python_binding():
