@@ -229,8 +229,10 @@ int leafk_instnorm_backward(const float* v, const float* stats, const float* gra
  * kernel on `stream` consumes clips as their slice lands, so the PCIe transfer and the compute
  * overlap without per-slice launch overheads; PCEN and the D2H copy follow on `stream`.  When
  * the FP32 kernel is selected, copy_stream == stream, or the driver lacks cuStreamWriteValue32,
- * it falls back to per-slice launches.  dev_x (B*T floats), dev_out (B*F*N floats) and workspace
- * are device scratch.  The call returns after enqueueing; the caller synchronises `stream`.
+ * it falls back to per-slice launches.  dev_x (B*T samples of cfg->input_format), dev_out (B*F*N elements of
+ * cfg->output_format) and workspace are device scratch; x_host / out_host hold the same element types (int16 PCM in
+ * halves the upload, LEAFK_OUTPUT_BF16 halves the read-back).  The call returns after enqueueing; the caller
+ * synchronises `stream`.
  * status_host (pinned host int, or NULL): receives the asynchronous error word together with the result (same stream
  * order as out_host) -- 0, or a code for leafk_status_message(): no extra synchronisation is needed to learn that a
  * slice of the copy stalled. */

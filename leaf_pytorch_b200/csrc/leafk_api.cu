@@ -321,6 +321,8 @@ int leafk_forward(const leafk_config* cfg, const leafk_params* prm, const float*
                               (long long)cfg->F * N, N, workspace, workspace_bytes, stream);
 }
 
+static size_t out_elem_bytes(const leafk_config* cfg) { return cfg->output_format == LEAFK_OUTPUT_BF16 ? 2 : 4; }
+
 // Sliced fallback of leafk_forward_host: slice i = H2D on copy_stream -> kernels on stream -> D2H.
 static int forward_host_sliced(const leafk_config* cfg, const leafk_params* prm, const float* x_host, int B, int T,
                                int N, float* out_host, int n_slices, float* dev_x, float* dev_out, void* workspace,
@@ -336,17 +338,18 @@ static int forward_host_sliced(const leafk_config* cfg, const leafk_params* prm,
     cudaEventCreateWithFlags(&up[made], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&done[made], cudaEventDisableTiming);
     const size_t esz = cfg->input_format == LEAFK_INPUT_S16 ? 2 : 4;
-    const size_t xoff = (size_t)b0 * T * esz;
+    const size_t osz = out_elem_bytes(cfg);
+    const size_t xoff = (size_t)b0 * T * esz, ooff = (size_t)b0 * cfg->F * N * osz;
     cudaError_t e = cudaMemcpyAsync((uint8_t*)dev_x + xoff, (const uint8_t*)x_host + xoff, esz * (size_t)nb * T,
                                     cudaMemcpyHostToDevice, cstream);
     if (e != cudaSuccess) { rc = fail(LEAFK_ECUDA, "H2D: %s", cudaGetErrorString(e)); ++made; break; }
     if (two) { cudaEventRecord(up[made], cstream); cudaStreamWaitEvent(stream, up[made], 0); }
-    rc = leafk_forward(cfg, prm, (const float*)((const uint8_t*)dev_x + xoff), nb, T, dev_out + (size_t)b0 * cfg->F * N,
+    rc = leafk_forward(cfg, prm, (const float*)((const uint8_t*)dev_x + xoff), nb, T, (float*)((uint8_t*)dev_out + ooff),
                        nullptr, workspace, workspace_bytes, stream);
     if (rc == LEAFK_OK) {
       if (two) { cudaEventRecord(done[made], stream); cudaStreamWaitEvent(cstream, done[made], 0); }
-      e = cudaMemcpyAsync(out_host + (size_t)b0 * cfg->F * N, dev_out + (size_t)b0 * cfg->F * N,
-                          sizeof(float) * (size_t)nb * cfg->F * N, cudaMemcpyDeviceToHost, two ? cstream : stream);
+      e = cudaMemcpyAsync((uint8_t*)out_host + ooff, (const uint8_t*)dev_out + ooff,
+                          osz * (size_t)nb * cfg->F * N, cudaMemcpyDeviceToHost, two ? cstream : stream);
       if (e != cudaSuccess) rc = fail(LEAFK_ECUDA, "D2H: %s", cudaGetErrorString(e));
     }
     ++made;
@@ -409,7 +412,7 @@ int leafk_forward_host(const leafk_config* cfg, const leafk_params* prm, const f
   rc = forward_impl(cfg, prm, dev_x, B, T, T, 0, T, 0, N, nullptr, nullptr, dev_out, nullptr, (long long)cfg->F * N, N,
                     workspace, workspace_bytes, stream, clips_per_flag, nullptr, nullptr);
   if (rc) return rc;
-  e = cudaMemcpyAsync(out_host, dev_out, sizeof(float) * (size_t)B * cfg->F * N, cudaMemcpyDeviceToHost, stream);
+  e = cudaMemcpyAsync(out_host, dev_out, out_elem_bytes(cfg) * (size_t)B * cfg->F * N, cudaMemcpyDeviceToHost, stream);
   if (e != cudaSuccess) return fail(LEAFK_ECUDA, "D2H: %s", cudaGetErrorString(e));
   if (status_host != nullptr) {                         // the asynchronous error word travels with the result
     e = cudaMemcpyAsync(status_host, workspace, sizeof(int), cudaMemcpyDeviceToHost, stream);
@@ -480,7 +483,7 @@ int leafk_forward_host_async(const leafk_config* cfg, const leafk_params* prm, c
   if (rc) return rc;
   cudaEventRecord(ev_compute_done, stream);
   cudaStreamWaitEvent(dstream, ev_compute_done, 0);
-  e = cudaMemcpyAsync(out_host, dev_out, sizeof(float) * (size_t)B * cfg->F * N, cudaMemcpyDeviceToHost, dstream);
+  e = cudaMemcpyAsync(out_host, dev_out, out_elem_bytes(cfg) * (size_t)B * cfg->F * N, cudaMemcpyDeviceToHost, dstream);
   if (e != cudaSuccess) return fail(LEAFK_ECUDA, "D2H: %s", cudaGetErrorString(e));
   if (status_host != nullptr) {                         // the asynchronous error word travels with the result
     e = cudaMemcpyAsync(status_host, workspace, sizeof(int), cudaMemcpyDeviceToHost, dstream);

@@ -451,7 +451,8 @@ def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, a
     ``n_slices`` pieces on a side stream, each followed by a stream-ordered flag write, and ONE
     persistent launch of the tensor-core kernel consumes clips as their slice lands (the FP32 kernel
     falls back to per-slice launches).  ``x_host``
-    (B,1,T) float32 CPU (pinned for full speed); returns ``out_host`` (B,F,N) pinned CPU.  The call
+    (B,1,T) float32 or int16 PCM, CPU (pinned for full speed); returns ``out_host`` (B,F,N) pinned CPU, float32 or
+    -- when ``spec.out_dtype`` is bfloat16 -- bf16 written by the PCEN kernel (half the read-back).  The call
     synchronises the compute stream before returning (the result is on the host)."""
     L = N.lib()
     if x_host.is_cuda or x_host.dtype not in (torch.float32, torch.int16) or x_host.dim() != 3 or x_host.shape[1] != 1:
@@ -462,23 +463,24 @@ def forward_host(spec: LeafSpec, x_host: torch.Tensor, kernel, pool_w, pool_b, a
     x_host = x_host.contiguous()
     B, _, T = x_host.shape
     n = spec.num_frames(T)
-    cfg = spec.config(x_host.dtype, out_dtype=torch.float32)
+    odt = spec.out_dtype
+    cfg = spec.config(x_host.dtype, out_dtype=odt)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, device)
     if out_host is None:
-        out_host = torch.empty((B, spec.F, n), dtype=torch.float32, pin_memory=True)
-    if out_host.is_cuda or out_host.dtype != torch.float32 or tuple(out_host.shape) != (B, spec.F, n) \
+        out_host = torch.empty((B, spec.F, n), dtype=odt, pin_memory=True)
+    if out_host.is_cuda or out_host.dtype != odt or tuple(out_host.shape) != (B, spec.F, n) \
             or not out_host.is_contiguous():
-        raise ValueError("out_host must be a contiguous float32 CPU tensor of shape (B,F,N)")
+        raise ValueError(f"out_host must be a contiguous {odt} CPU tensor of shape (B,F,N)")
     with torch.cuda.device(device):
         ws_bytes = L.leafk_workspace_bytes(C.byref(cfg), B, n)
-        key = (device.index, B, T, spec.F, spec.K, spec.H, spec.algo, n, x_host.dtype)
+        key = (device.index, B, T, spec.F, spec.K, spec.H, spec.algo, n, x_host.dtype, odt)
         with _host_cache_lock:
             bufs = _host_cache.get(key)
             if bufs is None or bufs[2].numel() < ws_bytes:
                 while len(_host_cache) >= _HOST_CACHE_MAX:          # bounded: drop the oldest shape, keep the rest
                     _host_cache.pop(next(iter(_host_cache)))
                 bufs = (torch.empty(B * T, dtype=x_host.dtype, device=device),
-                        torch.empty(B * spec.F * n, dtype=torch.float32, device=device),
+                        torch.empty(B * spec.F * n, dtype=odt, device=device),
                         torch.empty(ws_bytes, dtype=torch.uint8, device=device), torch.cuda.Stream(device=device),
                         torch.zeros(1, dtype=torch.int32).pin_memory())
                 _host_cache[key] = bufs

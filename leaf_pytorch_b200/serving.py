@@ -9,7 +9,7 @@ batch is already pipelined; this class removes the remaining per-call bubbles of
     pipe = HostPipeline(leaf, B, T, depth=2)
     t0 = pipe.submit(x0)                 # pinned (B,1,T) float32 or int16
     t1 = pipe.submit(x1)
-    y0 = pipe.result(t0)                 # pinned (B,F,N) float32, valid on return
+    y0 = pipe.result(t0)                 # pinned (B,F,N) float32 (bfloat16 if leaf.out_dtype is), valid on return
 """
 from __future__ import annotations
 
@@ -41,7 +41,8 @@ class HostPipeline:
             raise N.LeafNativeError("HostPipeline needs the module on a CUDA device; there is no CPU fallback")
         if not LF.tc_supported(self.spec.F, self.spec.K, self.spec.H) or self.spec.algo == "fp32":
             raise N.LeafNativeError("HostPipeline needs the tensor-core kernel (geometry not covered or algo='fp32')")
-        self.cfg = self.spec.config(input_dtype)
+        self.out_dtype = self.spec.out_dtype          # fixed at construction: the buffer sets are typed
+        self.cfg = self.spec.config(input_dtype, out_dtype=self.out_dtype)
         with torch.cuda.device(self.device):
             ws_bytes = self.lib.leafk_workspace_bytes(C.byref(self.cfg), self.B, self.n_frames)
             self.copy_stream = torch.cuda.Stream(device=self.device)
@@ -51,7 +52,7 @@ class HostPipeline:
             for _ in range(max(1, depth)):
                 s = _Set()
                 s.dev_x = torch.empty(self.B * self.T, dtype=input_dtype, device=self.device)
-                s.dev_out = torch.empty(self.B * self.spec.F * self.n_frames, dtype=torch.float32, device=self.device)
+                s.dev_out = torch.empty(self.B * self.spec.F * self.n_frames, dtype=self.out_dtype, device=self.device)
                 s.ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
                 s.ev_compute = self.lib.leafk_event_create()
                 s.ev_out = self.lib.leafk_event_create()
@@ -77,7 +78,11 @@ class HostPipeline:
         # pipeline's own streams must see those writes
         self.compute_stream.wait_stream(torch.cuda.current_stream(self.device))
         if out_host is None:
-            out_host = torch.empty((self.B, self.spec.F, self.n_frames), dtype=torch.float32, pin_memory=True)
+            out_host = torch.empty((self.B, self.spec.F, self.n_frames), dtype=self.out_dtype, pin_memory=True)
+        elif (out_host.is_cuda or out_host.dtype != self.out_dtype or not out_host.is_contiguous()
+              or tuple(out_host.shape) != (self.B, self.spec.F, self.n_frames)):
+            raise ValueError(f"out_host must be a contiguous CPU {self.out_dtype} tensor of shape "
+                             f"{(self.B, self.spec.F, self.n_frames)}")
         x_host = x_host.contiguous()
         prm_t = [None if p is None else p.detach() for p in self.leaf._param_tuple()]
         prm, keep = LF._params_struct(self.spec, *prm_t, self.device)

@@ -200,3 +200,35 @@ def test_bf16_output_and_b1fn_layout():
         got = fe(x)
     assert got.dtype == torch.bfloat16 and tuple(got.shape) == (5, 1, 40, 100)
     assert torch.equal(got[:, 0], ref.to(torch.bfloat16))
+
+
+def test_host_buffer_paths_with_bf16_features_and_int16_input():
+    """Host-buffer calls honour the module's output format: bf16 features come back as bf16 (half the read-back) and
+    equal the device path's bf16 features bit for bit -- pipelined flag path, sliced fallback and HostPipeline; int16 PCM
+    in at the same time."""
+    import leaf_pytorch_b200 as L
+    B, T = 6, 12000
+    x = bench_batch(B, T, seed=21)
+    pcm = (x * 32767.0).round().to(torch.int16)
+    fe = L.Leaf(out_dtype=torch.bfloat16).cuda()
+    with torch.no_grad():
+        want = fe(x.cuda()).cpu()
+        want_pcm = fe(pcm.cuda()).cpu()
+    assert want.dtype == torch.bfloat16
+    for n_slices in (1, 3):                                        # 1 = sliced fallback, 3 = ready-flag pipeline
+        got = fe.forward_host(x.pin_memory(), n_slices=n_slices)
+        assert got.dtype == torch.bfloat16 and torch.equal(got, want)
+        assert torch.equal(fe.forward_host(pcm.pin_memory(), n_slices=n_slices), want_pcm)
+    pipe = L.HostPipeline(fe, B, T, depth=2, n_slices=2, input_dtype=torch.int16)
+    tickets = [pipe.submit(pcm.pin_memory()) for _ in range(3)]
+    for t in tickets:
+        got = pipe.result(t)
+        assert got.dtype == torch.bfloat16 and torch.equal(got, want_pcm)
+    with pytest.raises(ValueError):
+        pipe.submit(pcm.pin_memory(), torch.empty((B, 40, fe.num_frames(T)), dtype=torch.float32).pin_memory())
+    pipe.close()
+    # float32 module, same buffers: unchanged behaviour
+    fe32 = L.Leaf().cuda()
+    fe32.load_state_dict(fe.state_dict())
+    got32 = fe32.forward_host(x.pin_memory(), n_slices=3)
+    assert got32.dtype == torch.float32 and torch.equal(got32.to(torch.bfloat16), want)
