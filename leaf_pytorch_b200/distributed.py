@@ -74,7 +74,10 @@ def shard_batch(x: torch.Tensor, rank: Optional[int] = None, world: Optional[int
 
 
 def frontend_parameters(leaf) -> List[torch.nn.Parameter]:
-    return [p for p in leaf._param_tuple() if p is not None]
+    """The module's own parameters in registration order: (pre-emphasis weight,) Gabor kernel, pooling width and bias,
+    alpha, delta, root, smoother coefficient -- the leaves that own the gradients (not the sorted view of the kernel
+    that sort_filters feeds to the kernels)."""
+    return list(leaf.parameters())
 
 
 def allreduce_frontend_grads(leaf, group=None, average: bool = True) -> Optional[torch.Tensor]:

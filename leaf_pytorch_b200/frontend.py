@@ -202,6 +202,14 @@ class Leaf(nn.Module):
     def num_frames(self, n_samples: int) -> int:
         return self.spec.num_frames(n_samples)
 
+    def _require_plain(self, what: str) -> None:
+        """The host-buffer, chunked and streaming entry points run the fused path only: with the optional stages around
+        it (pre-emphasis in front, mean/variance normalisation over all frames behind) they would silently compute
+        something else, so they refuse."""
+        if self._preemp is not None or self._instance_norm is not None:
+            raise NotImplementedError(f"{what} does not run the optional pre-emphasis / mean_var_norm stages; "
+                                      "use Leaf.forward for a module built with preemp=True or mean_var_norm=True")
+
     def _param_tuple(self):
         pc = self._compression
         kernel = self._complex_conv._kernel
@@ -234,14 +242,21 @@ class Leaf(nn.Module):
         its peak exceeds 1, peak-normalised -- the reference's per-clip transforms (utilities/data/raw_transforms.py:
         121-160, 334-344; utilities/data/utils.py:8-28) -- inside the kernels' own staging of the waveform.
         ``x_raw`` (B,1,Traw) float32 or int16 PCM on the GPU, ``raw_lengths`` (B,) true lengths."""
+        if self._preemp is not None:
+            # the clips are staged (cropped / padded / normalised) inside the Gabor kernel; a pre-emphasis belongs
+            # between the two, so it needs the prepared batch
+            raise NotImplementedError("forward_prepared cannot apply preemp=True on the fly; prepare the batch and call forward")
         prep = LF.prepare_clips(self.spec, x_raw, n_samples, raw_lengths, starts, pad_mode, peak_normalize)
         out = LF.leaf_forward(self.spec, x_raw, *self._param_tuple(), prep=prep)
+        if self._instance_norm is not None:
+            out = LF.instance_norm(out, self._instance_norm.eps)
         return out.unsqueeze(1) if self.out_layout == "b1fn" else out
 
     def forward_host(self, x_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
                      n_slices: int = 8) -> torch.Tensor:
         """Inference on host buffers: pinned (B,1,T) in -> pinned (B,F,N) out, H2D / kernels / D2H
         pipelined over batch slices inside the library (leafk_forward_host).  No autograd."""
+        self._require_plain("forward_host")
         prm = [None if p is None else p.detach() for p in self._param_tuple()]
         return LF.forward_host(self.spec, x_host, *prm, out_host=out_host, n_slices=n_slices,
                                device=self._complex_conv._kernel.device)

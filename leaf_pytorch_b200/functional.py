@@ -237,14 +237,14 @@ def forward_window(spec: LeafSpec, x_win, T_total: int, t_off: int, n_begin: int
         x_win = _check_input(x_win)
         ldx = x_win.shape[2]
     B, _, T_win = x_win.shape
-    cfg = spec.config(x_win.dtype, reuse_banks=reuse_banks)
     prm, keep = _params_struct(spec, kernel, pool_w, pool_b, alpha, delta, root, ema_w, x_win.device)
     with torch.cuda.device(x_win.device):
         if out is None:
-            out = torch.empty((B, spec.F, n_count), dtype=torch.float32, device=x_win.device)
-        if out.dtype != torch.float32 or out.dim() != 3 or out.shape[0] != B or out.shape[1] != spec.F \
-                or out.shape[2] != n_count or out.stride(2) != 1:
-            raise ValueError("out must be a float32 (B,F,n_count) view with unit stride along frames")
+            out = torch.empty((B, spec.F, n_count), dtype=spec.out_dtype, device=x_win.device)
+        if out.dtype not in (torch.float32, torch.bfloat16) or out.dim() != 3 or out.shape[0] != B \
+                or out.shape[1] != spec.F or out.shape[2] != n_count or out.stride(2) != 1:
+            raise ValueError("out must be a float32 / bfloat16 (B,F,n_count) view with unit stride along frames")
+        cfg = spec.config(x_win.dtype, reuse_banks=reuse_banks, out_dtype=out.dtype)   # the format follows the buffer
         state_out = None
         if spec.compression and want_state:
             state_out = torch.empty((B, spec.F), dtype=torch.float32, device=x_win.device)

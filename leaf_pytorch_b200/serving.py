@@ -30,6 +30,7 @@ class HostPipeline:
     def __init__(self, leaf, batch: int, n_samples: int, depth: int = 2, n_slices: int = 2,
                  input_dtype: torch.dtype = torch.float32, device=None):
         self.lib = N.lib()
+        leaf._require_plain("HostPipeline")
         self.leaf = leaf
         self.spec = leaf.spec
         self.B, self.T = int(batch), int(n_samples)

@@ -29,11 +29,12 @@ def needed_samples(spec: LF.LeafSpec, T_total: int, n_begin: int, n_count: int):
 def forward_chunked(leaf, x: torch.Tensor, chunk_frames: int = 1000) -> torch.Tensor:
     """Whole-clip features computed chunk by chunk over frames; ``x`` (B,1,T) is device resident.
     Peak scratch is that of one chunk instead of the whole clip.  No autograd."""
+    leaf._require_plain("forward_chunked")
     spec = leaf.spec
     prm = [None if p is None else p.detach() for p in leaf._param_tuple()]
     B, _, T = x.shape
     N = spec.num_frames(T)
-    out = torch.empty((B, spec.F, N), dtype=torch.float32, device=x.device)
+    out = torch.empty((B, spec.F, N), dtype=spec.out_dtype, device=x.device)     # bf16 features if the module asks
     if x.dtype not in (torch.float32, torch.int16) or not x.is_contiguous():
         x = LF._check_input(x)
     # one scratch buffer for every chunk: the banks written for the first chunk serve the others (same parameters),
@@ -58,6 +59,7 @@ class LeafStream:
     reference does at a clip's end (reference convolution.py:92, pooling.py:37)."""
 
     def __init__(self, leaf, batch: int, device=None):
+        leaf._require_plain("LeafStream")
         self.leaf = leaf
         self.spec = leaf.spec
         self.B = batch
@@ -94,7 +96,7 @@ class LeafStream:
         n_ready = (self.n_seen - 1 + 2 * pad_l - 2 * K + 2) // H + 1 if self.n_seen >= 2 * K - 1 - 2 * pad_l else 0
         n_ready = max(0, n_ready)
         if n_ready <= self.n_done:
-            return torch.empty((self.B, self.spec.F, 0), dtype=torch.float32, device=self.device)
+            return torch.empty((self.B, self.spec.F, 0), dtype=self.spec.out_dtype, device=self.device)
         # pretend the clip is very long: only frames whose window is complete are requested
         return self._emit(self.n_seen + (1 << 20), n_ready - self.n_done)
 
@@ -102,5 +104,5 @@ class LeafStream:
         """End of stream: emit the remaining frames with the true clip length."""
         N = self.spec.num_frames(self.n_seen) if self.n_seen > 0 else 0
         if N <= self.n_done:
-            return torch.empty((self.B, self.spec.F, 0), dtype=torch.float32, device=self.device)
+            return torch.empty((self.B, self.spec.F, 0), dtype=self.spec.out_dtype, device=self.device)
         return self._emit(self.n_seen, N - self.n_done)

@@ -232,3 +232,30 @@ def test_host_buffer_paths_with_bf16_features_and_int16_input():
     fe32.load_state_dict(fe.state_dict())
     got32 = fe32.forward_host(x.pin_memory(), n_slices=3)
     assert got32.dtype == torch.float32 and torch.equal(got32.to(torch.bfloat16), want)
+
+
+def test_chunked_and_streaming_paths_with_bf16_features():
+    """forward_chunked / LeafStream / forward_window follow the module's output format (the window call's format follows
+    its output buffer): bf16 features equal the float32 ones rounded."""
+    import leaf_pytorch_b200 as L
+    from leaf_pytorch_b200.streaming import forward_chunked, LeafStream
+    import leaf_pytorch_b200.functional as LF
+    x = bench_batch(3, 40000, seed=33).cuda()
+    fe = L.Leaf().cuda()
+    with torch.no_grad():
+        ref = forward_chunked(fe, x, chunk_frames=100)
+        whole = fe(x)
+        st = LeafStream(fe, 3)
+        ref_stream = torch.cat([st.push(x[:, :, i:i + 7000]) for i in range(0, 40000, 7000)] + [st.flush()], dim=2)
+        fe.out_dtype = torch.bfloat16
+        got = forward_chunked(fe, x, chunk_frames=100)
+        assert got.dtype == torch.bfloat16 and torch.equal(got, ref.to(torch.bfloat16))
+        st = LeafStream(fe, 3)
+        parts = [st.push(x[:, :, i:i + 7000]) for i in range(0, 40000, 7000)] + [st.flush()]
+        assert all(p.dtype == torch.bfloat16 for p in parts)
+        assert torch.equal(torch.cat(parts, dim=2), ref_stream.to(torch.bfloat16))
+        # explicit float32 buffer with a bf16 module: the buffer decides
+        prm = [None if p is None else p.detach() for p in fe._param_tuple()]
+        buf = torch.empty((3, 40, 250), dtype=torch.float32, device="cuda")
+        LF.forward_window(fe.spec, x, 40000, 0, 0, 250, *prm, out=buf)
+        assert torch.equal(buf, whole)

@@ -90,3 +90,40 @@ def test_numa_binding_helpers_are_safe_without_a_gpu():
     before = os.sched_getaffinity(0)
     assert D.bind_to_gpu_numa_node(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+def test_frontend_parameters_are_the_modules_own_leaves():
+    """With sort_filters the kernels see a sorted VIEW of the Gabor kernel; the all-reduce must address the leaf that owns
+    the gradient, and the pre-emphasis weight belongs to the frontend's parameters too."""
+    import leaf_pytorch_b200 as L
+    import leaf_pytorch_b200.distributed as D
+    fe = L.Leaf(n_filters=8, sort_filters=True, preemp=True)
+    ps = D.frontend_parameters(fe)
+    assert all(isinstance(p, torch.nn.Parameter) and p.is_leaf for p in ps)
+    assert sum(p.numel() for p in ps) == 8 * 8 + 2
+    assert [id(p) for p in ps] == [id(p) for p in fe.parameters()]
+    for p in ps:
+        p.grad = torch.full_like(p, 2.0)
+    flat = D.allreduce_frontend_grads(fe)                  # no process group: identity, but exercises the packing
+    assert flat.numel() == 66 and torch.all(flat == 2.0)
+
+
+def test_side_entry_points_refuse_modules_with_optional_stages():
+    """forward_host / HostPipeline / forward_chunked / LeafStream run the fused path only; with preemp or mean_var_norm
+    they must refuse instead of silently skipping the stage."""
+    import pytest
+    import leaf_pytorch_b200 as L
+    from leaf_pytorch_b200.streaming import forward_chunked, LeafStream
+    x = torch.zeros(1, 1, 4000)
+    for kw in ({"preemp": True}, {"mean_var_norm": True}):
+        fe = L.Leaf(n_filters=8, **kw)
+        with pytest.raises(NotImplementedError):
+            fe.forward_host(x)
+        with pytest.raises(NotImplementedError):
+            L.HostPipeline(fe, 1, 4000)
+        with pytest.raises(NotImplementedError):
+            forward_chunked(fe, x)
+        with pytest.raises(NotImplementedError):
+            LeafStream(fe, 1)
+    with pytest.raises(NotImplementedError):
+        L.Leaf(n_filters=8, preemp=True).forward_prepared(x, 2000)

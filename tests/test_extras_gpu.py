@@ -195,3 +195,19 @@ def test_classifier_logits_with_our_frontend_equal_logits_with_the_reference_fro
     clf.train()
     clf(x.cuda()).sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in clf.features.parameters())
+
+
+def test_prepared_forward_applies_mean_var_norm():
+    """forward_prepared runs the same stages as forward: with mean_var_norm=True the features are normalised."""
+    import leaf_pytorch_b200 as L
+    import leaf_pytorch_b200.functional as LF
+    g = torch.Generator().manual_seed(5)
+    raw = (torch.randn(4, 1, 9000, generator=g) * 0.7).cuda()
+    lens = torch.tensor([9000, 3000, 6000, 7001])
+    plain, normed = L.Leaf().cuda(), L.Leaf(mean_var_norm=True).cuda()
+    normed.load_state_dict(plain.state_dict())
+    with torch.no_grad():
+        a = plain.forward_prepared(raw, 6000, raw_lengths=lens)
+        b = normed.forward_prepared(raw, 6000, raw_lengths=lens)
+        assert torch.equal(b, LF.instance_norm(a, 1e-5))
+        assert b.mean(dim=2).abs().max().item() < 1e-4
