@@ -47,21 +47,30 @@ peak_divisor_kernel(const Geom g, const float* __restrict__ x, int only_too_loud
   }
 }
 
-// one block per clip: smallest raw sample over [0, length)
+// one block per clip: smallest raw sample over [0, length); NaN if the clip holds one (torch.min propagates it)
 __global__ void __launch_bounds__(256)
 clip_minimum_kernel(const Geom g, const float* __restrict__ x, float* __restrict__ min_out) {
   __shared__ float red[8];
+  __shared__ int red_nan[8];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ClipView cv = clip_view(g, b);
   float mn = 3.0e38f;
-  for (int i = tid; i < cv.len; i += blockDim.x) mn = fminf(mn, load_sample(x, cv.row, i, g.x_fmt));
+  int has_nan = 0;
+  for (int i = tid; i < cv.len; i += blockDim.x) {
+    const float v = load_sample(x, cv.row, i, g.x_fmt);
+    has_nan |= (v != v);
+    mn = fminf(mn, v);
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-  if (lane == 0) red[warp] = mn;
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    has_nan |= __shfl_xor_sync(0xffffffffu, has_nan, o);
+  }
+  if (lane == 0) { red[warp] = mn; red_nan[warp] = has_nan; }
   __syncthreads();
   if (tid == 0) {
-    for (int w = 1; w < 8; ++w) mn = fminf(mn, red[w]);
-    min_out[b] = cv.len > 0 ? mn : 0.f;
+    for (int w = 1; w < 8; ++w) { mn = fminf(mn, red[w]); has_nan |= red_nan[w]; }
+    min_out[b] = has_nan ? __int_as_float(0x7fc00000) : (cv.len > 0 ? mn : 0.f);
   }
 }
 

@@ -211,3 +211,21 @@ def test_prepared_forward_applies_mean_var_norm():
         b = normed.forward_prepared(raw, 6000, raw_lengths=lens)
         assert torch.equal(b, LF.instance_norm(a, 1e-5))
         assert b.mean(dim=2).abs().max().item() < 1e-4
+
+
+def test_clip_minimum_padding_propagates_nan_like_torch_min():
+    """PadToSize(mode='constant') pads with x.min(); torch.min returns NaN for a clip holding a NaN, so the padding --
+    and with it every frame of that clip -- is NaN, as when the transform runs on the CPU first."""
+    import leaf_pytorch_b200 as L
+    from oracle import leaf_oracle as O
+    n = 6000
+    raw = torch.randn(2, 1, 4000, generator=torch.Generator().manual_seed(3)) * 0.3
+    raw[1, 0, 3999] = float("nan")
+    prepared = torch.stack([O.prepare_clip(raw[b, 0].numpy(), n, "center", "min", peak_normalize=False) for b in range(2)]).unsqueeze(1)
+    assert torch.isnan(prepared[1, 0, 0]) and torch.isfinite(prepared[0]).all()
+    fe = L.Leaf().cuda()
+    with torch.no_grad():
+        got = fe.forward_prepared(raw.cuda(), n, pad_mode="min", peak_normalize=False).cpu()
+        same = fe(prepared.cuda()).cpu()
+    assert torch.isfinite(got[0]).all() and torch.isnan(got[1]).all()
+    assert torch.equal(torch.isnan(got), torch.isnan(same)) and torch.equal(got[0], same[0])
